@@ -1,0 +1,170 @@
+/*
+ * mulactseg_b200 -- C ABI of the B200-native superpixel-segmented scoring engine.
+ *
+ * This is the drop-in boundary for the hot path of sehyun03/MulActSeg named in
+ * BASELINE.json `north_star`.  The reference is pure Python: what it binds at
+ * this level is the third-party `torch_scatter` operator set plus the torch ops
+ * around it.  Each entry point below replaces one such operator chain; the
+ * comment above it cites the reference call sites (paths relative to the
+ * reference checkout).  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types.
+ *  - `*_dev` entry points take DEVICE pointers and enqueue on `stream`
+ *    (a `cudaStream_t` passed as void*; NULL = legacy default stream) without
+ *    synchronising.  `*_host` entry points take HOST pointers, do their own
+ *    host<->device copies and return after the result is in host memory.
+ *  - return value: 0 on success, a negative MAS_E_* code for argument errors,
+ *    a positive value = the cudaError_t that was raised.  `mas_last_error()`
+ *    returns a thread-local human-readable message for the last failure.
+ *  - there is NO CPU fallback: every compute entry point fails with a CUDA
+ *    error when no sm_100 device is present.
+ *  - images are NCHW-contiguous: logits[(img*C + c)*H*W + y*W + x].
+ */
+#ifndef MULACTSEG_B200_H
+#define MULACTSEG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAS_ABI_VERSION 1
+
+#define MAS_E_BADARG (-1)   /* null pointer / non-positive size / unsupported combination */
+#define MAS_E_RANGE (-2)    /* value out of the supported range (e.g. channels > MAS_MAX_CLASSES) */
+#define MAS_E_WORKSPACE (-3) /* workspace too small */
+
+#define MAS_MAX_CLASSES 32
+
+/* element type of the logits / feature tensors */
+#define MAS_F32 0
+#define MAS_BF16 1
+
+int mas_abi_version(void);
+const char* mas_last_error(void);
+
+/* ------------------------------------------------------------------ acquisition
+ *
+ * mas_bvsb_segment_stats_dev -- ONE pass over the logits of `n_img` images.
+ * Replaces, per batch (reference file:line):
+ *   F.softmax(preds/T) + torch.topk(prob,2) + ratio + 1e-8   active_selection/my_bvsb.py:19-27
+ *   torch_scatter.scatter(bvsb, spx, reduce='mean')           my_bvsb.py:73 (and the five sibling selectors)
+ *   F.one_hot(top1) + scatter(..., reduce='sum')              my_bvsb_banignore.py:44-45, my_bvsb_predclsbal_pwr*.py:68-69
+ *   torch.softmax(preds/T).mean(dim=(0,2,3))  (pass 1)        my_bvsb_predclsbal_pwr*.py:41-43
+ *
+ * For every pixel: (l1,top1),(l2) = best / second-best LOGIT (first index wins a tie),
+ * bvsb = exp((l2-l1)/T) + 1e-8  (== p2/p1 of the softmax), and
+ *   cls_sum[img][s][c] += bvsb   where s = ids[pixel], c = top1       (float32, atomics)
+ *   cls_cnt[img][s][c] += 1                                           (int32, exact)
+ *   prob_sum[img][c]   += softmax(l/T)[c]   for every c               (float64; skipped if NULL)
+ * Pixels whose id is outside [0, nseg) are ignored.  Outputs are ACCUMULATED
+ * into: the caller zeroes them (cudaMemsetAsync) before the first call.
+ * Region sums / counts / histograms / class means all follow from these tables
+ * (see mas_region_scores_dev), so the six selectors share this single pass.
+ * `image_stride` = elements between consecutive images of `logits` (0 = channels*height*width); a
+ * larger stride lets a channel-sliced view such as preds[:, :-1] (my_bvsb.py:65-66) be read in place.
+ */
+int mas_bvsb_segment_stats_dev(const void* logits, int logits_dtype, int64_t image_stride, const int32_t* ids,
+                               int n_img, int channels, int height, int width, int nseg,
+                               float temperature,
+                               float* cls_sum, int32_t* cls_cnt, double* prob_sum,
+                               void* stream);
+
+/* mas_region_scores_dev -- per-region epilogue over the tables above.
+ *   n[r]        = sum_c cls_cnt[r][c]
+ *   score[r]    = (sum_c w[c] * cls_sum[r][c]) / max(n[r], 1)     (w == NULL -> all ones)
+ *   dominant[r] = first arg-max_c cls_cnt[r][c]                    (0 for an empty region)
+ * Replaces the divide of scatter(reduce='mean') (my_bvsb.py:73), the cls_weight[top1] weighting
+ * (my_bvsb_predclsbal_pwr.py:59-65, re-associated) and hist.argmax(dim=1) (my_bvsb_banignore.py:60).
+ * `n_regions` = n_img * nseg.  `npix` and `dominant` may be NULL.
+ */
+int mas_region_scores_dev(const float* cls_sum, const int32_t* cls_cnt, const float* class_weight,
+                          int64_t n_regions, int channels,
+                          float* score, int32_t* npix, int32_t* dominant, void* stream);
+
+/* mas_minmax_nonzero_dev -- out[0] = min over entries != 0, out[1] = max over all entries
+ * (my_bvsb.py:80-81).  out[0] = +inf / out[1] = -inf when there is nothing to reduce. */
+int mas_minmax_nonzero_dev(const float* values, int64_t n, float* out2, void* stream);
+
+/* mas_dominant_hist_dev -- hist[c] += #regions with dominant == c (int64, `channels` bins;
+ * my_bvsb_clsbal_v2.py:64-66).  Accumulates: zero `hist` first. */
+int mas_dominant_hist_dev(const int32_t* dominant, int64_t n_regions, int channels, int64_t* hist, void* stream);
+
+/* mas_finalize_scores_dev -- in place, in the reference's order of operations:
+ *   if (minmax)  u = (u - minmax[0]) / (minmax[1] - minmax[0])   my_bvsb.py:80-81
+ *                (minmax = DEVICE pointer to {min over non-zero, max}; NULL = no normalisation)
+ *   if (ban_class >= 0 && dominant == ban_class) u = 0        my_bvsb_banignore.py:59-61
+ *   if (region_weight) u = region_weight[dominant] * u        my_bvsb_clsbal_v2.py:67-70
+ */
+int mas_finalize_scores_dev(float* score, const int32_t* dominant, int64_t n_regions,
+                            const float* minmax, int ban_class,
+                            const float* region_weight, void* stream);
+
+/* ------------------------------------------------------------------ top-k region selection
+ *
+ * Replaces `sorted(scores, reverse=True)` over (score, path, id) tuples
+ * (active_selection/base.py:37) restricted to the prefix that
+ * RegionActiveDataset.expand_training_set can consume
+ * (dataloader/region_active_dataset.py:31-73).
+ *
+ * mas_region_keys_dev builds one 64-bit key per region:
+ *   key = ordered_bits(score) << 32 | (image_rank[img] * nseg + id)
+ * where image_rank is the rank of the image's joined path string in ascending
+ * string order, so that descending key order == the reference's descending
+ * tuple order including ties.  Regions with in_pool == 0 get key 0 (never
+ * selected).  -0.0 is canonicalised to +0.0 (Python compares them equal).
+ *
+ * mas_topk_u64_dev writes the `k` largest non-zero keys of `keys[0..n)` to
+ * `out` (UNSORTED) and the number written to *out_count (min(k, #non-zero)).
+ * `workspace` needs mas_topk_workspace_bytes() bytes.  Keys must be distinct
+ * (they are, by construction) for the count to be exact.
+ */
+int mas_region_keys_dev(const float* score, const uint8_t* in_pool, const int32_t* image_rank,
+                        int64_t n_img, int nseg, uint64_t* keys, void* stream);
+size_t mas_topk_workspace_bytes(void);
+int mas_topk_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int32_t* out_count,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* mas_sort_desc_u64_dev -- in-place descending sort of n keys (n <= 2^22).  The buffer must have
+ * room for mas_sort_capacity(n) keys (n rounded up to a power of two, >= 2048): the tail is used as
+ * padding and holds zeros afterwards. */
+int64_t mas_sort_capacity(int64_t n);
+int mas_sort_desc_u64_dev(uint64_t* keys, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ host-buffer entries (end-to-end)
+ *
+ * mas_acquisition_host -- the whole scoring pass of one selector with HOST buffers.  Streams
+ * `n_img` images of logits + ids to the device in chunks of `chunk_img` images (double-buffered:
+ * the copy of chunk i+1 overlaps the kernel of chunk i), accumulates the tables on the device,
+ * then runs the selector epilogue and copies back
+ *   score    (n_img*nseg f32)
+ *   dominant (n_img*nseg i32, may be NULL)
+ *   prob_sum (n_img*channels f64, may be NULL; forced on for MAS_WEIGHT_PREDCLSBAL).
+ * `weighting`: MAS_WEIGHT_NONE, or MAS_WEIGHT_PREDCLSBAL = w_c = (coeff * pbar_c + 1)^-2 with pbar the
+ * mean over reference batches (`ref_batch` images each, the last one short) of the per-batch mean
+ * softmax probability (my_bvsb_predclsbal_pwr.py:36-47).
+ * `normalise` != 0: (u - min_nonzero) / (max - min_nonzero) (my_bvsb.py:80-81).
+ * `ban_class` >= 0: zero regions whose dominant arg-max class is ban_class.
+ * `clsbal` != 0: multiply by exp(-freq[dominant]) (my_bvsb_clsbal_v2.py:64-70).
+ * Host buffers should be pinned (cudaHostAlloc / cudaHostRegister) for the copies to overlap.
+ */
+#define MAS_WEIGHT_NONE 0
+#define MAS_WEIGHT_PREDCLSBAL 1
+int mas_acquisition_host(const void* logits, int logits_dtype, const int32_t* ids,
+                         int n_img, int channels, int height, int width, int nseg,
+                         float temperature, int weighting, float coeff, int ref_batch,
+                         int normalise, int ban_class, int clsbal, int chunk_img,
+                         float* score, int32_t* dominant, double* prob_sum);
+
+/* mas_select_topk_host -- host scores -> the k best (sorted descending) region keys, see
+ * mas_region_keys_dev for the key layout.  out_keys needs k slots; *out_count <= k. */
+int mas_select_topk_host(const float* score, const uint8_t* in_pool, const int32_t* image_rank,
+                         int64_t n_img, int nseg, int64_t k, uint64_t* out_keys, int32_t* out_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MULACTSEG_B200_H */

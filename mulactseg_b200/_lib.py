@@ -1,0 +1,70 @@
+"""ctypes binding of ``libmulactseg_b200.so`` (the C ABI of ``include/mulactseg_b200.h``).
+
+There is no CPU fallback anywhere in this package: if the shared library has not
+been built, or a compute entry point is called without an sm_100 device, the
+call raises.  ``python -m mulactseg_b200.build`` (or ``__graft_entry__.build()``)
+produces the library in-tree under ``mulactseg_b200/lib/``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmulactseg_b200.so")
+
+MAS_F32, MAS_BF16 = 0, 1
+
+# name -> (restype, argtypes); mirrors include/mulactseg_b200.h one to one
+SIGNATURES = {
+    "mas_abi_version": (c_int, []),
+    "mas_last_error": (c_char_p, []),
+    "mas_bvsb_segment_stats_dev": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                           c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mas_region_scores_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mas_minmax_nonzero_dev": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "mas_dominant_hist_dev": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "mas_finalize_scores_dev": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
+    "mas_region_keys_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "mas_topk_workspace_bytes": (c_size_t, []),
+    "mas_topk_u64_dev": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mas_sort_capacity": (c_int64, [c_int64]),
+    "mas_sort_desc_u64_dev": (c_int, [c_void_p, c_int64, c_void_p]),
+    "mas_acquisition_host": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_float,
+                                     c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mas_select_topk_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+class MulActSegError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MulActSegError(
+                f"{LIB_PATH} is missing: the CUDA extension has not been built "
+                "(run `python -m mulactseg_b200.build`); there is no CPU fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().mas_last_error()
+        raise MulActSegError(f"{what} failed (code {code}): {msg.decode() if msg else ''}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,87 @@
+"""Multi-GPU plumbing: shard the pool by image, exchange only the small pool-wide quantities.
+
+One process per GPU (``torch.distributed``, NCCL over NVLink on the GPU box; the same code runs over
+``gloo`` on CPU tensors in the tests).  The logits never cross GPUs -- the path shards by image with
+no data-path collective; what is exchanged:
+  * per-image class-probability sums           (N x C' f64, all_gather)   -> class weights
+  * min over non-zero / max of the scores      (2 floats, all_reduce)      -> normalisation
+  * dominant-class histogram                   (C' int64, all_reduce)      -> clsbal weights
+  * each rank's k best (score, region) keys    (k x 8 B, all_gather)       -> global top-k merge
+Every helper is the identity when ``group`` is None and torch.distributed is not initialised.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as td
+
+
+def is_distributed(group=None) -> bool:
+    return td.is_available() and td.is_initialized() and td.get_world_size(group) > 1
+
+
+def rank_world(group=None) -> Tuple[int, int]:
+    if td.is_available() and td.is_initialized():
+        return td.get_rank(group), td.get_world_size(group)
+    return 0, 1
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous image range of ``rank``: the first ``n % world`` ranks get one extra image."""
+    base, extra = divmod(int(n_items), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(n_items: int, world: int) -> List[int]:
+    return [shard_range(n_items, r, world)[1] - shard_range(n_items, r, world)[0] for r in range(world)]
+
+
+def all_gather_rows(local: torch.Tensor, group=None) -> torch.Tensor:
+    """Concatenate per-rank (n_r, ...) tensors along dim 0 in rank order (n_r may differ by rank)."""
+    if not is_distributed(group):
+        return local
+    world = td.get_world_size(group)
+    counts = torch.zeros(world, dtype=torch.int64, device=local.device)
+    counts[td.get_rank(group)] = local.shape[0]
+    td.all_reduce(counts, op=td.ReduceOp.SUM, group=group)
+    counts = counts.tolist()
+    width = max(counts)
+    padded = local.new_zeros((width,) + tuple(local.shape[1:]))
+    padded[: local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    td.all_gather(parts, padded.contiguous(), group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+def all_reduce_minmax(minmax: torch.Tensor, group=None) -> torch.Tensor:
+    """[min, max] pairs reduced over the ranks (+inf / -inf from an empty shard are neutral)."""
+    if not is_distributed(group):
+        return minmax
+    lo, hi = minmax[:1].clone(), minmax[1:].clone()
+    td.all_reduce(lo, op=td.ReduceOp.MIN, group=group)
+    td.all_reduce(hi, op=td.ReduceOp.MAX, group=group)
+    return torch.cat([lo, hi]).contiguous()
+
+
+def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
+    if is_distributed(group):
+        td.all_reduce(t, op=td.ReduceOp.SUM, group=group)
+    return t
+
+
+def gather_candidates(keys: torch.Tensor, count: torch.Tensor, k: int, group=None) -> torch.Tensor:
+    """All ranks' candidate keys -> one flat int64 tensor on every rank (unused slots are 0 = 'no key').
+
+    ``keys`` holds this rank's k best keys in its first ``count`` slots (anything after is ignored).
+    """
+    local = keys[:k].clone()
+    slot = torch.arange(k, device=keys.device)
+    local = torch.where(slot < count.to(torch.int64), local, torch.zeros_like(local))
+    if not is_distributed(group):
+        return local
+    world = td.get_world_size(group)
+    parts = [torch.empty_like(local) for _ in range(world)]
+    td.all_gather(parts, local.contiguous(), group=group)
+    return torch.cat(parts)

@@ -1,0 +1,161 @@
+"""Tensor-level wrappers over the C ABI: torch only provides device memory and the stream.
+
+Every function validates device / dtype / contiguity (``RuntimeError`` like the
+operators it replaces), passes raw pointers plus the current CUDA stream to the
+library and never synchronises.  No function here has a CPU path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _want(t: torch.Tensor, name: str, dtype=None, dims=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+    if dtype is not None and t.dtype not in (dtype if isinstance(dtype, tuple) else (dtype,)):
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if dims is not None and t.dim() != dims:
+        raise RuntimeError(f"{name}: expected {dims} dims, got shape {tuple(t.shape)}")
+
+
+def bvsb_segment_stats(logits: torch.Tensor, spx: torch.Tensor, nseg: int, temperature: float,
+                       cls_sum: torch.Tensor, cls_cnt: torch.Tensor, prob_sum: Optional[torch.Tensor]) -> None:
+    """Accumulate per-(image, superpixel, class) bvsb sums / counts (+ per-image softmax sums).
+
+    logits (B,C,H,W) f32|bf16, spx (B,H,W) i32, cls_sum/cls_cnt (B,nseg,C) f32/i32, prob_sum (B,C) f64 or None.
+    Outputs are accumulated into (zero them first).  See ``mas_bvsb_segment_stats_dev``.
+    """
+    if not isinstance(logits, torch.Tensor) or not logits.is_cuda:
+        raise RuntimeError("logits: expected a CUDA tensor (there is no CPU path)")
+    if logits.dim() != 4 or logits.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"logits: expected (B,C,H,W) float32/bfloat16, got {tuple(logits.shape)} {logits.dtype}")
+    _want(spx, "spx", torch.int32, 3)
+    b, c, h, w = logits.shape
+    # NCHW with dense planes; the image stride may exceed C*H*W (channel-sliced view, e.g. preds[:, :-1])
+    if b * c * h * w > 0 and (logits.stride(3) != 1 or logits.stride(2) != w or logits.stride(1) != h * w
+                              or (b > 1 and logits.stride(0) < c * h * w)):
+        raise RuntimeError("logits: expected NCHW layout with contiguous planes")
+    image_stride = logits.stride(0) if b > 1 else c * h * w
+    if tuple(spx.shape) != (b, h, w):
+        raise RuntimeError(f"spx shape {tuple(spx.shape)} does not match logits {tuple(logits.shape)}")
+    _want(cls_sum, "cls_sum", torch.float32)
+    _want(cls_cnt, "cls_cnt", torch.int32)
+    if cls_sum.numel() != b * nseg * c or cls_cnt.numel() != b * nseg * c:
+        raise RuntimeError("cls_sum / cls_cnt must hold B*nseg*C elements")
+    if prob_sum is not None:
+        _want(prob_sum, "prob_sum", torch.float64)
+        if prob_sum.numel() != b * c:
+            raise RuntimeError("prob_sum must hold B*C elements")
+    with torch.cuda.device(logits.device):
+        _lib.call("mas_bvsb_segment_stats_dev", logits.data_ptr(),
+                  _lib.MAS_F32 if logits.dtype == torch.float32 else _lib.MAS_BF16, int(image_stride), spx.data_ptr(),
+                  b, c, h, w, int(nseg), float(temperature), cls_sum.data_ptr(), cls_cnt.data_ptr(),
+                  _ptr(prob_sum), _stream(logits))
+
+
+def region_scores(cls_sum: torch.Tensor, cls_cnt: torch.Tensor, class_weight: Optional[torch.Tensor] = None,
+                  want_npix: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
+    """(score, npix | None, dominant), each shaped like cls_sum without its last dim."""
+    _want(cls_sum, "cls_sum", torch.float32)
+    _want(cls_cnt, "cls_cnt", torch.int32)
+    c = cls_sum.shape[-1]
+    shape = cls_sum.shape[:-1]
+    n = cls_sum.numel() // c
+    if class_weight is not None:
+        _want(class_weight, "class_weight", torch.float32)
+        if class_weight.numel() != c:
+            raise RuntimeError("class_weight must have C elements")
+    score = torch.empty(shape, dtype=torch.float32, device=cls_sum.device)
+    dominant = torch.empty(shape, dtype=torch.int32, device=cls_sum.device)
+    npix = torch.empty(shape, dtype=torch.int32, device=cls_sum.device) if want_npix else None
+    with torch.cuda.device(cls_sum.device):
+        _lib.call("mas_region_scores_dev", cls_sum.data_ptr(), cls_cnt.data_ptr(), _ptr(class_weight), n, c,
+                  score.data_ptr(), _ptr(npix), dominant.data_ptr(), _stream(cls_sum))
+    return score, npix, dominant
+
+
+def minmax_nonzero(values: torch.Tensor) -> torch.Tensor:
+    """Device tensor [min over non-zero entries, max over all entries]."""
+    _want(values, "values", torch.float32)
+    out = torch.empty(2, dtype=torch.float32, device=values.device)
+    with torch.cuda.device(values.device):
+        _lib.call("mas_minmax_nonzero_dev", values.data_ptr(), values.numel(), out.data_ptr(), _stream(values))
+    return out
+
+
+def dominant_hist(dominant: torch.Tensor, channels: int) -> torch.Tensor:
+    _want(dominant, "dominant", torch.int32)
+    hist = torch.zeros(channels, dtype=torch.int64, device=dominant.device)
+    with torch.cuda.device(dominant.device):
+        _lib.call("mas_dominant_hist_dev", dominant.data_ptr(), dominant.numel(), int(channels), hist.data_ptr(),
+                  _stream(dominant))
+    return hist
+
+
+def finalize_scores(score: torch.Tensor, dominant: Optional[torch.Tensor], minmax: Optional[torch.Tensor] = None,
+                    ban_class: int = -1, region_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """In-place normalise / ban / re-weight (the reference's order of operations)."""
+    _want(score, "score", torch.float32)
+    if dominant is not None:
+        _want(dominant, "dominant", torch.int32)
+    if minmax is not None:
+        _want(minmax, "minmax", torch.float32)
+    if region_weight is not None:
+        _want(region_weight, "region_weight", torch.float32)
+    with torch.cuda.device(score.device):
+        _lib.call("mas_finalize_scores_dev", score.data_ptr(), _ptr(dominant), score.numel(), _ptr(minmax),
+                  int(ban_class), _ptr(region_weight), _stream(score))
+    return score
+
+
+def region_keys(score: torch.Tensor, in_pool: torch.Tensor, image_rank: torch.Tensor) -> torch.Tensor:
+    """(N,S) scores -> (N*S,) uint64-as-int64 keys; 0 for regions outside the pool."""
+    _want(score, "score", torch.float32, 2)
+    _want(in_pool, "in_pool", torch.uint8, 2)
+    _want(image_rank, "image_rank", torch.int32, 1)
+    n, s = score.shape
+    if tuple(in_pool.shape) != (n, s) or image_rank.numel() != n:
+        raise RuntimeError("in_pool / image_rank shape mismatch")
+    keys = torch.empty(n * s, dtype=torch.int64, device=score.device)
+    with torch.cuda.device(score.device):
+        _lib.call("mas_region_keys_dev", score.data_ptr(), in_pool.data_ptr(), image_rank.data_ptr(), n, s,
+                  keys.data_ptr(), _stream(score))
+    return keys
+
+
+def sort_capacity(n: int) -> int:
+    return int(_lib.load().mas_sort_capacity(int(n)))
+
+
+def topk_keys(keys: torch.Tensor, k: int, sort: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The k largest non-zero keys (sorted descending if ``sort``) and a device int32 count.
+
+    The returned buffer has ``sort_capacity(k)`` slots; slots past the count hold zeros when sorted.
+    """
+    _want(keys, "keys", torch.int64, 1)
+    k = int(k)
+    cap = sort_capacity(max(k, 1))
+    out = torch.zeros(cap, dtype=torch.int64, device=keys.device)
+    count = torch.zeros(1, dtype=torch.int32, device=keys.device)
+    ws_bytes = int(_lib.load().mas_topk_workspace_bytes())
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+    with torch.cuda.device(keys.device):
+        _lib.call("mas_topk_u64_dev", keys.data_ptr(), keys.numel(), k, out.data_ptr(), count.data_ptr(),
+                  ws.data_ptr(), ws_bytes, _stream(keys))
+        if sort and k > 1:
+            _lib.call("mas_sort_desc_u64_dev", out.data_ptr(), k, _stream(keys))
+    return out, count

@@ -1,0 +1,86 @@
+"""Global top-k region selection and the pool/label bookkeeping around it.
+
+Reference behaviour being reproduced (file:line relative to the reference checkout):
+  * ``sorted(scores, reverse=True)`` over ``(score, 'img,lbl,spx', id)`` tuples -- active_selection/base.py:37
+  * ``RegionActiveDataset.expand_training_set`` walking that list until the cumulative cost exceeds the
+    budget -- dataloader/region_active_dataset.py:16-73
+Only the first ``budget + 1`` entries of the 6 M-entry sorted list can ever be consumed (every region
+costs >= 1), so the device selects and sorts exactly those (``ops.topk_keys``) and the host never sees
+the rest.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import dist as mdist
+from . import ops
+
+
+def image_ranks(im_idx: Sequence[Sequence[str]]) -> np.ndarray:
+    """rank[i] = position of image i's joined path in ascending string order (ties in the tuple sort)."""
+    joined = [",".join(k) for k in im_idx]
+    order = sorted(range(len(joined)), key=joined.__getitem__)
+    rank = np.empty(len(joined), dtype=np.int32)
+    rank[np.asarray(order, dtype=np.int64)] = np.arange(len(joined), dtype=np.int32)
+    return rank
+
+
+def pool_mask(im_idx: Sequence[Sequence[str]], suppix: Dict[str, List[int]], nseg: int,
+              lo: int = 0, hi: Optional[int] = None) -> np.ndarray:
+    """(hi-lo, nseg) uint8: 1 where the region is still in the unlabeled pool (my_bvsb.py:44-46)."""
+    hi = len(im_idx) if hi is None else hi
+    mask = np.zeros((hi - lo, nseg), dtype=np.uint8)
+    for row, key in enumerate(im_idx[lo:hi]):
+        ids = suppix.get(key[2])
+        if ids:
+            mask[row, np.asarray(ids, dtype=np.int64)] = 1
+    return mask
+
+
+def decode_keys(keys: np.ndarray, nseg: int, im_idx: Sequence[Sequence[str]], rank: np.ndarray):
+    """uint64 keys -> [(score, 'img,lbl,spx', id)] in the given order (see ``mas_region_keys_dev``)."""
+    keys = np.ascontiguousarray(keys).view(np.uint64)
+    hi = (keys >> np.uint64(32)).astype(np.uint32)
+    tie = (keys & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    bits = np.where(hi & np.uint32(0x80000000), hi & np.uint32(0x7FFFFFFF), ~hi).astype(np.uint32)
+    scores = bits.view(np.float32).astype(np.float64).tolist()
+    image_of_rank = np.empty(len(rank), dtype=np.int64)
+    image_of_rank[rank] = np.arange(len(rank))
+    imgs = image_of_rank[tie // nseg].tolist()
+    ids = (tie % nseg).tolist()
+    joined = {}
+    out = []
+    for s, i, r in zip(scores, imgs, ids):
+        path = joined.get(i)
+        if path is None:
+            path = joined[i] = ",".join(im_idx[i])
+        out.append((s, path, int(r)))
+    return out
+
+
+def top_regions(scores: torch.Tensor, in_pool: torch.Tensor, image_rank_local: torch.Tensor, k: int, group=None):
+    """Sorted (descending) keys of the k best pool regions over ALL ranks, as a host uint64 array.
+
+    scores / in_pool: this rank's (n_local, S) shard; image_rank_local: global ranks of its images.
+    Per rank: key -> radix-select k -> all_gather (k x 8 B per rank) -> select + sort k on every rank.
+    """
+    keys = ops.region_keys(scores, in_pool, image_rank_local)
+    if mdist.is_distributed(group):
+        local, count = ops.topk_keys(keys, k, sort=False)
+        merged = mdist.gather_candidates(local, count, k, group)
+        best, count = ops.topk_keys(merged, k, sort=True)
+    else:
+        best, count = ops.topk_keys(keys, k, sort=True)
+    n = int(count.item())
+    return best[:n].cpu().numpy().view(np.uint64)
+
+
+def cumulative_cut(costs: np.ndarray, budget: int) -> int:
+    """Length of the prefix expand_training_set consumes: stop AFTER the pick that makes the running
+    cost exceed the budget (strict '>', region_active_dataset.py:66); the whole list if it never does."""
+    running = np.cumsum(costs.astype(np.int64))
+    over = np.nonzero(running > budget)[0]
+    return int(over[0]) + 1 if over.size else int(len(costs))

@@ -1,0 +1,51 @@
+"""Shared test scaffolding: fake trainer / pool objects shaped like the reference's."""
+import types
+
+import numpy as np
+import torch
+
+
+class IdentityNet:
+    """The acquisition tests hand logits over as 'images', so the network is the identity."""
+
+    def eval(self):
+        return self
+
+    def __call__(self, x):
+        return x
+
+
+class PoolSet(torch.utils.data.Dataset):
+    def __init__(self, logits, spx, im_idx, suppix):
+        self.logits, self.spx = logits, spx
+        self.im_idx = [list(k) for k in im_idx]
+        self.suppix = {k: list(v) for k, v in suppix.items()}
+
+    def __len__(self):
+        return len(self.im_idx)
+
+    def __getitem__(self, i):
+        return {"images": self.logits[i], "spx": self.spx[i], "labels": self.spx[i]}
+
+
+def selector_args(method, nseg, num_classes, predignore, temp, coeff, bs):
+    return types.SimpleNamespace(val_batch_size=bs, val_num_workers=0, nseg=nseg, active_method=method,
+                                 num_classes=num_classes, ce_temp=temp, cls_weight_coeff=coeff, save_scores=False,
+                                 method="active_joint_multi_predignore_lossdecomp" if predignore
+                                 else "active_joint_multi_lossdecomp")
+
+
+def fake_trainer(device):
+    return types.SimpleNamespace(net=IdentityNet(), device=torch.device(device), model_save_dir="/tmp", selection_iter=1)
+
+
+def batches(logits, spx, bs):
+    return [(logits[i:i + bs], spx[i:i + bs]) for i in range(0, logits.shape[0], bs)]
+
+
+def assert_scores_close(got, ref, normalised, msg=""):
+    """1e-5 relative (north_star).  Normalised selectors subtract the pool minimum, so entries near that
+    minimum lose relative accuracy by cancellation: allow 2e-6 absolute on the [0,1] scale there."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2e-6 if normalised else 1e-12, err_msg=msg)
