@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the superpixel-segmented scoring hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+Workload (BASELINE.json configs[1]): one ``my_bvsb_predclsbal_pwr`` acquisition round over a synthetic
+Cityscapes-shaped pool -- 1024x2048 logits with 19 classes (fp32), 2048 superpixels per image,
+``val_batch_size`` 4, ``cls_weight_coeff`` 6, T = 0.1, budget 100 000 class-units with fair counting --
+sharded by image: 372 images per GPU (2975 / 8 rounded up), so N = 8 is the full pool (weak scaling).
+A *step* is one whole round over the resident shard: zero the tables, stream every image's logits through
+the fused scorer (one launch per batch of 4 images, as the selector plugin does), class weights (NCCL
+all-gather of the per-image class-probability sums), per-region scores, per-GPU top-(budget+1) radix
+select, NCCL all-gather of the candidates, merge + sort, copy the winners to the host and cut the prefix
+by cumulative label cost.  ``value`` = regions scored+selected per second over all GPUs.
+
+One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H, W, C, NSEG = 1024, 2048, 19, 2048
+TEMP, COEFF, REF_BATCH, BUDGET = 0.1, 6.0, 4, 100_000
+METRIC = "superpixel regions scored+selected/sec"
+UNIT = "regions/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images-per-gpu", type=int, default=372)
+    ap.add_argument("--e2e-images", type=int, default=24, help="images per GPU in the host-buffer (e2e) step")
+    ap.add_argument("--cpu-images", type=int, default=8, help="images in the bounded CPU-baseline sample")
+    ap.add_argument("--coherent", type=int, default=0, help="draw logits at 1/k resolution and up-sample (0 = i.i.d.)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([p.strip() for p in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_inputs(n_img: int, seed: int = 0):
+    from mulactseg_b200 import synth
+    return (synth.logits(n_img, C, H, W, "cosine", seed=seed), synth.superpixel_map(n_img, H, W, NSEG, "jitter", seed=seed + 1))
+
+
+def cpu_round(n_img: int, seed: int = 0, inputs=None):
+    """The reference's CPU implementation of the path (oracle port: same torch ops, all host threads) on a
+    bounded sample of the workload.  Returns (regions, seconds, phases)."""
+    from mulactseg_b200 import synth
+    from oracle import acquisition as oa
+    logits, spx = inputs if inputs is not None else cpu_inputs(n_img, seed)
+    im_idx, suppix = synth.pool_lists(n_img, NSEG)
+    rng = np.random.RandomState(seed)
+    cost = rng.randint(1, 4, size=(n_img, NSEG))
+    index_of = {k[2]: i for i, k in enumerate(im_idx)}
+    pool = [(logits[i:i + REF_BATCH], spx[i:i + REF_BATCH]) for i in range(0, n_img, REF_BATCH)]
+    t0 = time.perf_counter()
+    scores = oa.scores_predclsbal_pwr(pool, NSEG, TEMP, COEFF, ban_ignore=False)
+    t1 = time.perf_counter()
+    ranked = oa.rank_regions(oa.score_list(im_idx, suppix, scores))
+    t2 = time.perf_counter()
+    budget = max(1, int(BUDGET * n_img / 2975))
+    oa.expand_training_set(ranked, budget, [], {}, [list(k) for k in im_idx], {k: list(v) for k, v in suppix.items()},
+                           lambda p, s: cost[index_of[p], s])
+    t3 = time.perf_counter()
+    return n_img * NSEG, t3 - t0, {"score_s": t1 - t0, "sort_s": t2 - t1, "select_s": t3 - t2}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    n_img = REF_BATCH   # one reference batch per step keeps the whole arm within a few minutes
+    inputs = cpu_inputs(n_img)
+    for _ in range(min(args.warmup, 1)):
+        cpu_round(n_img, inputs=inputs)
+    times, phases = [], None
+    for i in range(args.steps):
+        regions, sec, phases = cpu_round(n_img, inputs=inputs)
+        times.append(sec)
+    ms = 1e3 * float(np.mean(times))
+    value = n_img * NSEG / (ms / 1e3)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, n_img, note="CPU arm: each step is a bounded sample of the workload"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_img} images of {H}x{W}x{C} per step (oracle port of the reference's torch ops: "
+                                   f"two passes, sorted(), expand_training_set); phases {json.dumps({k: round(v, 3) for k, v in phases.items()})}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, images_per_gpu, note=""):
+    return {"workload": "configs[1]: my_bvsb_predclsbal_pwr acquisition round, synthetic Cityscapes-shaped pool",
+            "images_per_gpu": images_per_gpu, "height": H, "width": W, "classes": C, "nseg": NSEG,
+            "val_batch_size": REF_BATCH, "cls_weight_coeff": COEFF, "temperature": TEMP, "budget": BUDGET,
+            "fair_counting": True, "logits": "tanh(N(0,1))*0.9" + (f", coherent/{args.coherent}" if args.coherent else ", i.i.d."),
+            "superpixels": "jittered 32x64 grid", "sharding": f"by image, dp{args.gpus}",
+            "l2": "inputs (>= 4 GB per GPU) exceed the 126 MB L2; no flush needed", "note": note}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch.distributed as td
+    from mulactseg_b200 import _lib, acquisition as acq, dist as mdist, ops, selection, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback in mulactseg_b200")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    n_loc = args.images_per_gpu
+    n_tot = n_loc * world
+    P = H * W
+    spec = acq.SELECTORS["my_bvsb_predclsbal_pwr"]
+
+    # ---- resident inputs (generated on the device, per chunk to bound temporaries)
+    logits = torch.empty((n_loc, C, H, W), dtype=torch.float32, device=dev)
+    spx = torch.empty((n_loc, H, W), dtype=torch.int32, device=dev)
+    chunk = 12
+    for i in range(0, n_loc, chunk):
+        m = min(chunk, n_loc - i)
+        logits[i:i + m] = synth.logits(m, C, H, W, "cosine", seed=1000 * rank + i, device=dev, coherent=args.coherent)
+        spx[i:i + m] = synth.superpixel_map(m, H, W, NSEG, "jitter", seed=7000 * rank + i, device=dev, dtype=torch.int32)
+    # pool bookkeeping inputs: every region in the pool, image rank = global index, synthetic label costs
+    in_pool = torch.ones((n_loc, NSEG), dtype=torch.uint8, device=dev)
+    image_rank = torch.arange(rank * n_loc, (rank + 1) * n_loc, dtype=torch.int32, device=dev)
+    cost_all = np.random.RandomState(0).randint(1, 4, size=(n_tot * NSEG,)).astype(np.int64)
+    k_sel = BUDGET + 1
+    stats = acq.RegionStats(n_loc, NSEG, C, dev, need_prob=True)
+    ev_pairs = []
+
+    def step(record_events: bool):
+        stats.zero_()
+        for i in range(0, n_loc, REF_BATCH):
+            if record_events:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            stats.add_batch(i, logits[i:i + REF_BATCH], spx[i:i + REF_BATCH], TEMP)
+            if record_events:
+                e1.record()
+                ev_pairs.append((e0, e1, min(REF_BATCH, n_loc - i)))
+        scores, _ = acq.finalize(stats, spec, COEFF, REF_BATCH, None)
+        keys = selection.top_regions(scores, in_pool, image_rank, k_sel, None)   # host uint64, sorted descending
+        tie = (keys & np.uint64(0xFFFFFFFF)).astype(np.int64)                    # == global region index here
+        return selection.cumulative_cut(cost_all[tie], BUDGET)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        picked = step(False)
+    sync_all()
+    launches0 = lib.mas_kernel_launches()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.cudart().cudaProfilerStart()   # no-op unless run under `ncu --profile-from-start off`
+    wall0 = time.perf_counter()
+    t_start.record()
+    for _ in range(args.steps):
+        picked = step(True)
+    t_end.record()
+    sync_all()
+    wall = time.perf_counter() - wall0
+    torch.cuda.cudart().cudaProfilerStop()
+    clocks = sampler.stop() if sampler else None
+    launches = lib.mas_kernel_launches() - launches0
+    ms_total = torch.tensor([max(t_start.elapsed_time(t_end), 0.0)], device=dev, dtype=torch.float64)
+    if world > 1:
+        td.all_reduce(ms_total, op=td.ReduceOp.MAX)
+    ms_step = float(ms_total.item()) / args.steps
+    value = n_tot * NSEG / (ms_step / 1e3)
+
+    # dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events on the launch stream)
+    bytes_per_img = P * (C * 4 + 4) + NSEG * C * 8
+    dur = np.array([a.elapsed_time(b) for a, b, _ in ev_pairs])
+    imgs = np.array([m for _, _, m in ev_pairs])
+    full = imgs == REF_BATCH
+    achieved = float(np.mean(bytes_per_img * imgs[full] / (dur[full] * 1e-3))) / 1e9
+    peak, peak_src = peaks()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "bvsb_stats_kernel<19,f32,vec4,prob>", "peak_source": peak_src + ", burst",
+                "bytes_per_launch": int(bytes_per_img * REF_BATCH), "mean_launch_ms": float(np.mean(dur[full])),
+                "kernel_share_of_step": float(dur.sum() / args.steps / ms_step)}
+
+    # ---- end-to-end through the C ABI with HOST buffers (H2D of logits + ids inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        n_e = min(args.e2e_images, n_loc)
+        h_logits = torch.empty((n_e, C, H, W), dtype=torch.float32).pin_memory()
+        h_spx = torch.empty((n_e, H, W), dtype=torch.int32).pin_memory()
+        h_logits.copy_(logits[:n_e]); h_spx.copy_(spx[:n_e])
+        torch.cuda.synchronize()
+        h_score = np.empty(n_e * NSEG, dtype=np.float32)
+        h_pool = np.ones(n_e * NSEG, dtype=np.uint8)
+        h_rank = np.arange(n_e, dtype=np.int32)
+        k_e = min(int(BUDGET * n_e / n_loc / 8) + 1, n_e * NSEG)
+        h_keys = np.zeros(k_e, dtype=np.uint64)
+        h_cnt = np.zeros(1, dtype=np.int32)
+
+        def e2e_step():
+            _lib.call("mas_acquisition_host", h_logits.data_ptr(), 0, h_spx.data_ptr(), n_e, C, H, W, NSEG, TEMP, 1, COEFF,
+                      REF_BATCH, 0, -1, 0, REF_BATCH, h_score.ctypes.data, None, None)
+            _lib.call("mas_select_topk_host", h_score.ctypes.data, h_pool.ctypes.data, h_rank.ctypes.data, n_e, NSEG, k_e,
+                      h_keys.ctypes.data, h_cnt.ctypes.data)
+            return selection.cumulative_cut(cost_all[(h_keys[: int(h_cnt[0])] & np.uint64(0xFFFFFFFF)).astype(np.int64)], k_e - 1)
+
+        e2e_step()
+        sync_all()
+        n_rep = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(n_rep):
+            e2e_step()
+        sync_all()
+        sec = torch.tensor([(time.perf_counter() - t0) / n_rep], device=dev, dtype=torch.float64)
+        if world > 1:
+            td.all_reduce(sec, op=td.ReduceOp.MAX)
+        e2e = {"value": world * n_e * NSEG / float(sec.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(n_e * P * (C * 4 + 4) + n_e * NSEG * 5 + n_e * 4),
+               "d2h_bytes_per_step": int(n_e * NSEG * 4 + k_e * 8 + 4),
+               "images_per_gpu": n_e, "ms_per_step": 1e3 * float(sec.item()),
+               "api": "mas_acquisition_host + mas_select_topk_host (C ABI, pinned host buffers, chunked double-buffered H2D)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        n_c = max(REF_BATCH, args.cpu_images)
+        regions, sec, phases = cpu_round(n_c)
+        cpu = {"value": regions / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n_c} of the {n_loc} images ({regions} regions) in {sec:.1f} s: "
+                         f"{json.dumps({k: round(v, 2) for k, v in phases.items()})}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(args, n_loc), "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "wall_ms_per_step": 1e3 * wall / args.steps,
+                "selected_regions": int(picked)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,8 @@ extern "C" {
 
 int mas_abi_version(void);
 const char* mas_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench bookkeeping) */
+int64_t mas_kernel_launches(void);
 
 /* ------------------------------------------------------------------ acquisition
  *

@@ -20,6 +20,7 @@ MAS_F32, MAS_BF16 = 0, 1
 SIGNATURES = {
     "mas_abi_version": (c_int, []),
     "mas_last_error": (c_char_p, []),
+    "mas_kernel_launches": (c_int64, []),
     "mas_bvsb_segment_stats_dev": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                                            c_void_p, c_void_p, c_void_p, c_void_p]),
     "mas_region_scores_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -222,6 +222,7 @@ cudaError_t launch_stats(const StatsParams& p, cudaStream_t stream) {
     const long long blocks = (p.total_tiles + kWarps - 1) / kWarps;
     const size_t smem = (size_t)p.C * kThreads * sizeof(uint2);
     bvsb_stats_kernel<CMAX, EXACT, VEC, NEED_PROB, T><<<(unsigned)blocks, kThreads, smem, stream>>>(p);
+    mas::count_launches(1);
     return cudaGetLastError();
 }
 
@@ -381,6 +382,7 @@ extern "C" int mas_region_scores_dev(const float* cls_sum, const int32_t* cls_cn
     const long long blocks = (n_regions + threads - 1) / threads;
     region_scores_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(cls_sum, cls_cnt, class_weight, n_regions,
                                                                                  channels, score, npix, dominant);
+    mas::count_launches(1);
     MAS_LAUNCH_OK("region_scores_kernel");
     return 0;
 }
@@ -391,6 +393,7 @@ extern "C" int mas_minmax_nonzero_dev(const float* values, int64_t n, float* out
     // the two ordered keys live in the caller's output buffer while reducing (same size: 2 x 32 bit)
     uint32_t* bits = reinterpret_cast<uint32_t*>(out2);
     minmax_init_kernel<<<1, 1, 0, st>>>(bits);
+    mas::count_launches(n > 0 ? 3 : 2);
     if (n > 0) {
         const int threads = 256;
         const long long blocks = std::min<long long>((n + threads - 1) / threads, (long long)mas::sm_count() * 8);
@@ -409,6 +412,7 @@ extern "C" int mas_dominant_hist_dev(const int32_t* dominant, int64_t n_regions,
     const long long blocks = std::min<long long>((n_regions + threads - 1) / threads, (long long)mas::sm_count() * 4);
     dominant_hist_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(dominant, n_regions, channels,
                                                                                  reinterpret_cast<unsigned long long*>(hist));
+    mas::count_launches(1);
     MAS_LAUNCH_OK("dominant_hist_kernel");
     return 0;
 }
@@ -422,6 +426,7 @@ extern "C" int mas_finalize_scores_dev(float* score, const int32_t* dominant, in
     const long long blocks = (n_regions + threads - 1) / threads;
     finalize_scores_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(score, dominant, n_regions, minmax,
                                                                                    ban_class, region_weight);
+    mas::count_launches(1);
     MAS_LAUNCH_OK("finalize_scores_kernel");
     return 0;
 }

@@ -11,6 +11,7 @@
 namespace mas {
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);  // bookkeeping for mas_kernel_launches()
 
 inline int cuda_fail(cudaError_t e, const char* what) {
     set_error("%s: %s", what, cudaGetErrorString(e));

@@ -163,6 +163,7 @@ extern "C" int mas_region_keys_dev(const float* score, const uint8_t* in_pool, c
     const int threads = 256;
     region_keys_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
         score, in_pool, image_rank, n, nseg, reinterpret_cast<unsigned long long*>(keys));
+    mas::count_launches(1);
     MAS_LAUNCH_OK("region_keys_kernel");
     return 0;
 }
@@ -178,6 +179,7 @@ extern "C" int mas_topk_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint
     SelectState* state = reinterpret_cast<SelectState*>(workspace);
     const unsigned long long* kk = reinterpret_cast<const unsigned long long*>(keys);
     select_init_kernel<<<1, 256, 0, st>>>(state, k);
+    mas::count_launches((n > 0 && k > 0) ? 2 + 16 + 1 : 2);
     if (n > 0 && k > 0) {
         const int threads = 256;
         const unsigned blocks = (unsigned)std::min<long long>((n + threads - 1) / threads, (long long)mas::sm_count() * 8);
@@ -206,14 +208,19 @@ extern "C" int mas_sort_desc_u64_dev(uint64_t* keys, int64_t n, void* stream) {
     long long n_pad = kSortTile;
     while (n_pad < n) n_pad <<= 1;
     unsigned long long* kk = reinterpret_cast<unsigned long long*>(keys);
-    if (n_pad > n) sort_pad_kernel<<<(unsigned)((n_pad - n + 255) / 256), 256, 0, st>>>(kk, n, n_pad);
+    int launches = 1;
+    if (n_pad > n) { sort_pad_kernel<<<(unsigned)((n_pad - n + 255) / 256), 256, 0, st>>>(kk, n, n_pad); ++launches; }
     const unsigned tiles = (unsigned)(n_pad / kSortTile);
     sort_tile_kernel<<<tiles, kSortThreads, 0, st>>>(kk);
     for (long long k = 2ll * kSortTile; k <= n_pad; k <<= 1) {
-        for (long long j = k >> 1; j >= kSortTile; j >>= 1)
+        for (long long j = k >> 1; j >= kSortTile; j >>= 1) {
             sort_global_step_kernel<<<(unsigned)((n_pad / 2 + 255) / 256), 256, 0, st>>>(kk, n_pad, k, j);
+            ++launches;
+        }
         sort_tile_merge_kernel<<<tiles, kSortThreads, 0, st>>>(kk, k);
+        ++launches;
     }
+    mas::count_launches(launches);
     MAS_LAUNCH_OK("sort_desc_u64 kernels");
     return 0;
 }

@@ -60,6 +60,8 @@ def bvsb_segment_stats(logits: torch.Tensor, spx: torch.Tensor, nseg: int, tempe
         _want(prob_sum, "prob_sum", torch.float64)
         if prob_sum.numel() != b * c:
             raise RuntimeError("prob_sum must hold B*C elements")
+    if b == 0:
+        return
     with torch.cuda.device(logits.device):
         _lib.call("mas_bvsb_segment_stats_dev", logits.data_ptr(),
                   _lib.MAS_F32 if logits.dtype == torch.float32 else _lib.MAS_BF16, int(image_stride), spx.data_ptr(),
