@@ -54,9 +54,14 @@ def test_selectors_match_reference_golden(case):
 
 @pytest.mark.parametrize("shape", [(3, 20, 128, 256, 512, "jitter"), (2, 21, 65, 77, 40, "jitter"),
                                    (2, 19, 64, 128, 2048, "random"), (1, 5, 33, 36, 7, "grid"),
-                                   (2, 32, 40, 64, 30, "jitter"), (1, 2, 16, 32, 4, "grid")])
+                                   (2, 32, 40, 64, 30, "jitter"), (1, 2, 16, 32, 4, "grid"),
+                                   (5, 20, 24, 200, 64, "jitter"), (3, 22, 37, 132, 150, "jitter"),
+                                   (9, 19, 8, 260, 16, "grid")])
 @pytest.mark.parametrize("method", ["my_bvsb_predclsbal_pwr_banignore", "my_bvsb_clsbal_v2"])
-def test_selectors_match_oracle(shape, method):
+@pytest.mark.parametrize("path", ["tma", "ldg"])
+def test_selectors_match_oracle(shape, method, path, monkeypatch):
+    """Both data paths of the scorer (TMA ring where rows are 16-byte aligned, LDG otherwise / when forced)."""
+    monkeypatch.setenv("MAS_SCORER_PATH", path)
     n, c, h, w, nseg, kind = shape
     logits = synth.logits(n, c, h, w, "cosine", seed=n * c + h)
     spx = synth.superpixel_map(n, h, w, nseg, kind, seed=7, drop_ids=1 if nseg > 4 else 0)
@@ -89,8 +94,12 @@ def test_bf16_logits_match_oracle_on_rounded_inputs():
     assert np.isfinite(score.numpy()).all() and ref.shape == score.shape
 
 
-def test_full_size_properties():
+@pytest.mark.parametrize("path,stages,warps", [("tma", "", ""), ("tma", "3", "5"), ("ldg", "", "")])
+def test_full_size_properties(path, stages, warps, monkeypatch):
     """Cityscapes-shaped images: size-independent invariants instead of the (slow) oracle."""
+    monkeypatch.setenv("MAS_SCORER_PATH", path)
+    monkeypatch.setenv("MAS_SCORER_STAGES", stages)
+    monkeypatch.setenv("MAS_SCORER_WARPS", warps)
     n, c, h, w, nseg = 2, 20, 1024, 2048, 2048
     logits = synth.logits(n, c, h, w, "cosine", seed=1, device=DEV)
     spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=2, device=DEV, dtype=torch.int32)
