@@ -43,6 +43,9 @@ extern "C" {
 /* element type of the logits / feature tensors */
 #define MAS_F32 0
 #define MAS_BF16 1
+/* element type of superpixel id maps (the reference hands int64 maps over: ext_transforms.py:389,406) */
+#define MAS_I32 0
+#define MAS_I64 1
 
 int mas_abi_version(void);
 const char* mas_last_error(void);
@@ -165,6 +168,90 @@ int mas_acquisition_host(const void* logits, int logits_dtype, const int32_t* id
  * mas_region_keys_dev for the key layout.  out_keys needs k slots; *out_count <= k. */
 int mas_select_topk_host(const float* score, const uint8_t* in_pool, const int32_t* image_rank,
                          int64_t n_img, int nseg, int64_t k, uint64_t* out_keys, int32_t* out_count);
+
+/* ------------------------------------------------------------------ stage-1 losses (forward + backward)
+ *
+ * Replaces, in ONE pass over the logits of the masked pixels (reference file:line):
+ *   F.softmax(inputs/T) + permute + per-image boolean compaction        utils/loss.py:99-118, :550-568
+ *   torch_scatter.scatter(valid_output, valid_spx, reduce='max')        utils/loss.py:122,
+ *        trainer/active_joint_multi_predignore.py:109, ..._mclossablation2.py:60          (group / MIL loss)
+ *   targets[spx] gather, (prob * trg).sum(1), -log(. + 1e-8)            utils/loss.py:572-581,
+ *        trainer/active_joint_multi_predignore_lossdecomp.py:52-70, active_joint_multi_lossdecomp.py:37-56
+ *
+ * mas_multihot_info_dev -- per (image, superpixel) candidate word from the multi-hot targets
+ * (n_regions x target_channels, uint8):
+ *   bits 0..channels-1 : targets[r][c] != 0      (channels < target_channels reproduces targets[..., :-1])
+ *   bit 31             : the region takes part in the group loss: MAS_GROUP_ALL always,
+ *                        MAS_GROUP_ONLYMULTI iff sum_c targets[r][c] over ALL target_channels > 1
+ *                        (is_trg_multi, ..._mclossablation2.py:35)
+ */
+#define MAS_MAX_LOSS_CLASSES 31
+#define MAS_GROUP_ALL 0
+#define MAS_GROUP_ONLYMULTI 1
+int mas_multihot_info_dev(const uint8_t* targets, int64_t n_regions, int target_channels, int channels, int group_mode,
+                          uint32_t* info, void* stream);
+
+/* mas_multihot_loss_fwd_dev -- logits (n_img, channels, H, W) f32 contiguous, ids (n_img, H, W) int32|int64,
+ * mask (n_img, H, W) uint8 (non-zero = selected pixel), info from mas_multihot_info_dev.  A pixel counts when
+ * its mask is set and 0 <= id < nseg (the crop-padding id == nseg never counts).  With P = softmax(x / T),
+ * row = candidate set of the pixel's superpixel, pos = sum_{c in row} P_c, l = -log(pos + 1e-8):
+ *   MAS_LOSS_CHOICE: acc[0] += sum l, acc[1] += #pixels with |row| == 1      (one-hot bucket)
+ *                    acc[2], acc[3]: |row| > 1 (multi-hot bucket);  acc[4], acc[5]: |row| == 0
+ *   MAS_LOSS_GROUP : group_max[(img*nseg + s)*channels + c] = max over the masked pixels of group regions of
+ *                    (bits(P_c) << 32 | ~pixel) for c in row  -- value and first arg-max pixel of the
+ *                    max-pool; then acc[6] += sum -log(M + 1e-8) over entries with M > 0, acc[7] += their number.
+ * `acc` (8 doubles) is ACCUMULATED into and `group_max` must be zero on entry (cudaMemsetAsync both).
+ * The reference's losses follow as  sum / (1 + count)  per bucket (counters start at 1).
+ */
+#define MAS_LOSS_CHOICE 1
+#define MAS_LOSS_GROUP 2
+int mas_multihot_loss_fwd_dev(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask, const uint32_t* info,
+                              int n_img, int channels, int height, int width, int nseg, float temperature, int flags,
+                              double* acc, uint64_t* group_max, void* stream);
+
+/* mas_multihot_loss_bwd_dev -- dense gradient of  coef[0]*acc[0] + coef[1]*acc[2] + coef[2]*acc[4] + coef[3]*acc[6]
+ * with respect to the logits (coef = 4 DEVICE floats; the caller folds the 1/(1+count) factors and the loss
+ * coefficients in).  The group term reaches only the arg-max pixel of each counted (superpixel, class), like the
+ * autograd of torch_scatter's max.  grad_logits (n_img, channels, H, W) f32 is fully written (zeros elsewhere).
+ */
+int mas_multihot_loss_bwd_dev(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask, const uint32_t* info,
+                              const uint64_t* group_max, const float* coef, int n_img, int channels, int height, int width,
+                              int nseg, float temperature, int flags, float* grad_logits, void* stream);
+
+/* ------------------------------------------------------------------ stage-2 pseudo-labellers
+ *
+ * mas_candidate_argmax_dev -- trainer/eval_within_multihot.py:93-146 top_pseudo_label_generation:
+ *   labels[pixel] = first arg-max over c of logit[c] * targets[spx[pixel]][c] on selected pixels (mask set,
+ *   0 <= id < nseg), 255 elsewhere.  Non-candidate classes contribute 0 (not -inf), exactly like the reference's
+ *   multiply-then-max.  logits (n_img, channels, H, W) f32, info from mas_multihot_info_dev, labels (n_img, H, W) u8.
+ */
+int mas_candidate_argmax_dev(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask, const uint32_t* info,
+                             int n_img, int channels, int height, int width, int nseg, uint8_t* labels, void* stream);
+
+/* mas_proto_labeller_dev -- ONE image of ActiveTrainer.pseudo_label_generation
+ * (trainer/eval_save_cosplbl_prop.py:121-314 with only_multihot = 1; the shipped
+ * trainer/eval_save_cosplbl_prop_includeonehot.py:121-316 with only_multihot = 0):
+ *   selected pixel  = mask set, 0 <= id < nseg (and, only_multihot: its superpixel has > 1 candidate class);
+ *   prototype(s,c)  = feats[:, first arg-max over the selected pixels of s of softmax(logits)[c]]  for c in targets[s];
+ *   selected pixels : label = class of the prototype of their OWN superpixel with the largest inner product (first on ties);
+ *   threshold(s,c)  = lower median (MAS_THRESHOLD_MEDIAN, torch.median) or minimum (MAS_THRESHOLD_MIN) of those largest
+ *                     inner products over the pixels assigned to prototype (s,c); 1.0 if none;
+ *   other pixels    : among the selected superpixels s whose 3x3-dilated mask reaches the pixel's superpixel (s itself
+ *                     included), the LARGEST s with  threshold(s,k) < <prototype(s,k), feat[pixel]>  for some k labels the
+ *                     pixel with the class of its best prototype (== the reference's ascending overwrite order, :276-305);
+ *   everything else : 255.
+ * feats (feat_channels, H, W) f32, logits (channels, H, W) f32, targets (nseg, target_channels) u8 (the first `channels`
+ * columns are the candidate sets), labels (H, W) u8.  status[0] (device int32) = number of selected pixels whose
+ * superpixel has no candidate class -- the reference raises on such input (:226); callers should too.
+ * `workspace`: 256-byte aligned device buffer of mas_proto_labeller_workspace_bytes() bytes.
+ */
+#define MAS_THRESHOLD_MEDIAN 0
+#define MAS_THRESHOLD_MIN 1
+size_t mas_proto_labeller_workspace_bytes(int feat_channels, int channels, int height, int width, int nseg);
+int mas_proto_labeller_dev(const float* feats, int feat_channels, const float* logits, int channels,
+                           const uint8_t* targets, int target_channels, const uint8_t* mask, const void* ids, int ids_dtype,
+                           int height, int width, int nseg, int only_multihot, int threshold_mode,
+                           uint8_t* labels, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

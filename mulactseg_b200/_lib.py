@@ -15,6 +15,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmulactseg_b200.so")
 
 MAS_F32, MAS_BF16 = 0, 1
+MAS_I32, MAS_I64 = 0, 1
+MAS_GROUP_ALL, MAS_GROUP_ONLYMULTI = 0, 1
+MAS_LOSS_CHOICE, MAS_LOSS_GROUP = 1, 2
+MAS_MAX_LOSS_CLASSES = 31
+MAS_THRESHOLD_MEDIAN, MAS_THRESHOLD_MIN = 0, 1
 
 # name -> (restype, argtypes); mirrors include/mulactseg_b200.h one to one
 SIGNATURES = {
@@ -35,6 +40,16 @@ SIGNATURES = {
     "mas_acquisition_host": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_float,
                                      c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mas_select_topk_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
+    "mas_multihot_info_dev": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mas_multihot_loss_fwd_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                          c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "mas_candidate_argmax_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                         c_void_p, c_void_p]),
+    "mas_proto_labeller_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "mas_proto_labeller_dev": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                       c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mas_multihot_loss_bwd_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                          c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,528 @@
+// Stage-2 pseudo-labellers: prototype labeller (P1) and candidate arg-max labeller (P2).
+//
+// Reference (paths relative to the reference checkout):
+//   P1  trainer/eval_save_cosplbl_prop.py:121-314 pseudo_label_generation (prototypes from multi-hot superpixels only)
+//       trainer/eval_save_cosplbl_prop_includeonehot.py:121-316 (shipped: every selected superpixel)
+//   P2  trainer/eval_within_multihot.py:93-146 top_pseudo_label_generation
+//
+// What the reference does per image, and what runs here instead:
+//   softmax + scatter_max(prob, spx)  -> arg-max pixel per (superpixel, candidate class)        [losses.cu pass, T = 1]
+//   prototypes = feat[arg-max pixel]                                                             [proto_gather_kernel]
+//   dense mm(protos, valid_feat.T) (nproto x HW') + scatter_max over it, of which only the block of a pixel's OWN
+//   superpixel is consumed                      -> per superpixel: sims of its own pixels only   [proto_assign_kernel]
+//   per-prototype torch.median / min of the similarities assigned to it                          [same kernel, radix select]
+//   per-superpixel skimage binary_dilation on the CPU + torch.unique -> neighbour ids            [spx_adjacency_kernel: bit matrix]
+//   python loop over selected superpixels, mm(protos_s, feat[Q].T), ordered overwrite            [proto_propagate_kernel]
+// The sequential "later superpixels overwrite earlier ones" (:276-305) becomes: every unselected pixel takes the label
+// offered by the LARGEST adjacent selected superpixel id whose threshold test passes; selected pixels keep the label
+// of their own superpixel's nearest prototype (:309-310).
+//
+// Similarities are fp32 FMA chains over the feature channels in a FIXED order (channel 0..F-1), the same in the
+// assign and the propagate kernel, so that "threshold < similarity" is evaluated on bit-identical numbers for the
+// pixel that defines the threshold.  The contraction is tiny (|protos_s| <= C', typically 1-3, per pixel) and bound by
+// reading the (F, H, W) features of the touched superpixels once: no tensor cores.
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace {
+
+constexpr uint32_t kGroupBit = 0x80000000u;
+constexpr int kAssignThreads = 256;
+constexpr int kGroup = 8;          // prototypes evaluated per pass over a pixel's feature column
+
+struct LabelParams {
+    const float* feats;     // (F, H, W)
+    const uint8_t* mask;    // (H, W)
+    const void* ids;        // (H, W)
+    int F, C, H, W, S, P;
+    int threshold_min;      // 0: lower median, 1: min
+    const uint32_t* info;               // (S)
+    const unsigned long long* gmax;     // (S, C)
+    const int* offset;                  // (S + 1) CSR offsets
+    const int* pixlist;                 // (P) pixels grouped by superpixel
+    float* proto;                       // (S, C, F)
+    float* own_sim;                     // (P)
+    uint8_t* own_cls;                   // (P)
+    float* thr;                         // (S, C)
+    uint32_t* adj;                      // (S, words)
+    uint32_t* svalid;                   // (words) selected superpixels that own prototypes
+    int words;
+    uint8_t* labels;                    // (H, W)
+};
+
+template <typename IdT>
+__device__ __forceinline__ int read_id(const void* ids, size_t i, int S) {
+    const long long v = (long long)reinterpret_cast<const IdT*>(ids)[i];
+    return (v < 0 || v >= S) ? -1 : (int)v;
+}
+
+__device__ __forceinline__ float ordered_to_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// ------------------------------------------------------------------------------------------ P2
+template <typename IdT>
+__global__ void candidate_argmax_kernel(const float* __restrict__ logits, const void* __restrict__ ids, const uint8_t* __restrict__ mask,
+                                        const uint32_t* __restrict__ info, long long n_pix, int P, int C, int S,
+                                        uint8_t* __restrict__ labels) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += (long long)gridDim.x * blockDim.x) {
+        uint8_t out = 255;
+        if (mask[i]) {
+            const int img = (int)(i / P);
+            const int id = read_id<IdT>(ids, (size_t)i, S);
+            if (id >= 0) {
+                const uint32_t bits = info[(size_t)img * S + id];
+                const float* x = logits + (size_t)img * C * P + (i - (long long)img * P);
+                // arg-max over c of logit * target (first index on ties): non-candidates contribute 0, not -inf
+                float best = ((bits & 1u) ? x[0] : 0.f);
+                int arg = 0;
+                for (int c = 1; c < C; ++c) {
+                    const float v = ((bits >> c) & 1u) ? x[(size_t)c * P] : 0.f;
+                    if (v > best) { best = v; arg = c; }
+                }
+                out = (uint8_t)arg;
+            }
+        }
+        labels[i] = out;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ CSR of pixels by superpixel
+// lanes holding a run of equal ids aggregate into one atomic; run members keep their order (coalescing later)
+__device__ __forceinline__ void run_info(int id, int lane, int& head_lane, int& run_len) {
+    const int prev = __shfl_up_sync(0xffffffffu, id, 1);
+    const bool head = lane == 0 || id != prev;
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    head_lane = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+    const unsigned above = heads & ~(0xffffffffu >> (31 - head_lane));   // heads after this run's head
+    const int next = above ? (__ffs(above) - 1) : 32;
+    run_len = next - head_lane;
+}
+
+template <typename IdT>
+__global__ void spx_count_kernel(const void* __restrict__ ids, int P, int S, int* __restrict__ count) {
+    const int lane = threadIdx.x & 31;
+    const long long padded = ((long long)P + 31) & ~31ll;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += (long long)gridDim.x * blockDim.x) {
+        const int id = i < P ? read_id<IdT>(ids, (size_t)i, S) : -1;
+        int head_lane, run_len;
+        run_info(id, lane, head_lane, run_len);
+        if (lane == head_lane && id >= 0) atomicAdd(count + id, run_len);
+    }
+}
+
+// exclusive scan of count[0..S) into offset[0..S]; also clears the fill cursors
+__global__ void spx_scan_kernel(const int* __restrict__ count, int S, int* __restrict__ offset, int* __restrict__ cursor) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < S; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < S ? count[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const int before = carry + (warp ? warp_sums[warp - 1] : 0) + x - v;
+        if (i < S) { offset[i] = before; cursor[i] = 0; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offset[S] = carry;
+}
+
+template <typename IdT>
+__global__ void spx_fill_kernel(const void* __restrict__ ids, int P, int S, const int* __restrict__ offset, int* __restrict__ cursor,
+                                int* __restrict__ pixlist) {
+    const int lane = threadIdx.x & 31;
+    const long long padded = ((long long)P + 31) & ~31ll;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += (long long)gridDim.x * blockDim.x) {
+        const int id = i < P ? read_id<IdT>(ids, (size_t)i, S) : -1;
+        int head_lane, run_len;
+        run_info(id, lane, head_lane, run_len);
+        int base = 0;
+        if (lane == head_lane && id >= 0) base = atomicAdd(cursor + id, run_len);
+        base = __shfl_sync(0xffffffffu, base, head_lane);
+        if (id >= 0) pixlist[offset[id] + base + (lane - head_lane)] = (int)i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ adjacency (3x3 dilation)
+__device__ __forceinline__ void adj_set(uint32_t* adj, int words, int a, int b) {
+    uint32_t* w = adj + (size_t)a * words + (b >> 5);
+    const uint32_t bit = 1u << (b & 31);
+    if (!(*reinterpret_cast<volatile uint32_t*>(w) & bit)) atomicOr(w, bit);
+}
+
+template <typename IdT>
+__global__ void spx_adjacency_kernel(const void* __restrict__ ids, int H, int W, int S, int words, uint32_t* adj) {
+    const long long P = (long long)H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+        const int a = read_id<IdT>(ids, (size_t)i, S);
+        if (a < 0) continue;
+        // right, down-left, down, down-right: every 8-neighbour pair is seen once
+        const int dx[4] = {1, -1, 0, 1}, dy[4] = {0, 1, 1, 1};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xx = x + dx[k], yy = y + dy[k];
+            if (xx < 0 || xx >= W || yy >= H) continue;
+            const int b = read_id<IdT>(ids, (size_t)yy * W + xx, S);
+            if (b < 0 || b == a) continue;
+            adj_set(adj, words, a, b);
+            adj_set(adj, words, b, a);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ prototypes
+// one warp per (superpixel, class): copy the feature column of the arg-max-probability pixel
+__global__ void proto_gather_kernel(LabelParams p) {
+    const long long entry = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (entry >= (long long)p.S * p.C) return;
+    const int s = (int)(entry / p.C), c = (int)(entry - (long long)s * p.C);
+    const uint32_t inf = p.info[s];
+    if (!(inf & kGroupBit) || !((inf >> c) & 1u)) return;
+    const unsigned long long e = p.gmax[entry];
+    if (e == 0ull) return;
+    const uint32_t pix = ~(uint32_t)e;
+    for (int ch = lane; ch < p.F; ch += 32) p.proto[entry * p.F + ch] = p.feats[(size_t)ch * p.P + pix];
+    if (lane == 0) atomicOr(p.svalid + (s >> 5), 1u << (s & 31));
+}
+
+__device__ __forceinline__ bool pixel_selected(const LabelParams& p, int pix, uint32_t inf) {
+    return (inf & kGroupBit) && p.mask[pix] != 0;
+}
+
+// dot products of pixel `pix` with the kGroup prototypes staged in shared memory (fixed channel order)
+__device__ __forceinline__ void dot_group(const LabelParams& p, const float* sproto, int pix, float (&acc)[kGroup]) {
+#pragma unroll
+    for (int g = 0; g < kGroup; ++g) acc[g] = 0.f;
+    const float* f = p.feats + pix;
+#pragma unroll 4
+    for (int ch = 0; ch < p.F; ++ch) {
+        const float x = __ldg(f + (size_t)ch * p.P);
+#pragma unroll
+        for (int g = 0; g < kGroup; ++g) acc[g] = fmaf(x, sproto[g * p.F + ch], acc[g]);
+    }
+}
+
+// stage prototypes k0 .. k0+kGroup-1 of superpixel s (classes in ascending order) into shared memory
+__device__ __forceinline__ void stage_protos(const LabelParams& p, float* sproto, int s, uint32_t bits, int k0, int* scls) {
+    // class of the k-th candidate
+    if (threadIdx.x < kGroup) {
+        uint32_t b = bits;
+        int c = -1;
+        for (int k = 0; k <= k0 + (int)threadIdx.x && b; ++k) { c = __ffs(b) - 1; b &= b - 1u; if (k < k0 + (int)threadIdx.x) c = -1; }
+        scls[threadIdx.x] = c;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kGroup * p.F; i += blockDim.x) {
+        const int g = i / p.F, ch = i - g * p.F;
+        const int c = scls[g];
+        sproto[i] = c >= 0 ? p.proto[((size_t)s * p.C + c) * p.F + ch] : 0.f;
+    }
+    __syncthreads();
+}
+
+// one CTA per selected superpixel: nearest prototype of every selected pixel, then the per-prototype threshold
+__global__ void __launch_bounds__(kAssignThreads) proto_assign_kernel(LabelParams p) {
+    extern __shared__ float sproto[];          // [kGroup][F]
+    __shared__ int scls[kGroup];
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int sel_prefix, sel_rank;
+    __shared__ float red[kAssignThreads / 32];
+    const int s = blockIdx.x;
+    if (!((p.svalid[s >> 5] >> (s & 31)) & 1u)) return;
+    const uint32_t inf = p.info[s];
+    const uint32_t bits = inf & ~kGroupBit;
+    const int K = __popc(bits);
+    const int beg = p.offset[s], end = p.offset[s + 1];
+
+    for (int k0 = 0; k0 < K; k0 += kGroup) {
+        stage_protos(p, sproto, s, bits, k0, scls);
+        for (int e = beg + threadIdx.x; e < end; e += blockDim.x) {
+            const int pix = p.pixlist[e];
+            if (!pixel_selected(p, pix, inf)) continue;
+            float acc[kGroup];
+            dot_group(p, sproto, pix, acc);
+            float best = k0 == 0 ? -INFINITY : p.own_sim[pix];
+            int bestc = k0 == 0 ? 255 : p.own_cls[pix];
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g) {
+                if (scls[g] >= 0 && (acc[g] > best || bestc == 255)) { best = acc[g]; bestc = scls[g]; }
+            }
+            p.own_sim[pix] = best;
+            p.own_cls[pix] = (uint8_t)bestc;
+            if (k0 + kGroup >= K) p.labels[pix] = (uint8_t)bestc;
+        }
+        __syncthreads();
+    }
+
+    // thresholds: lower median (torch.median) or min of the similarities of the pixels assigned to each prototype
+    uint32_t b = bits;
+    while (b) {
+        const int c = __ffs(b) - 1;
+        b &= b - 1u;
+        float result;
+        if (p.threshold_min) {
+            float mn = INFINITY;
+            for (int e = beg + threadIdx.x; e < end; e += blockDim.x) {
+                const int pix = p.pixlist[e];
+                if (pixel_selected(p, pix, inf) && p.own_cls[pix] == c) mn = fminf(mn, p.own_sim[pix]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mn;
+            __syncthreads();
+            mn = red[0];
+            for (int w = 1; w < kAssignThreads / 32; ++w) mn = fminf(mn, red[w]);
+            result = mn == INFINITY ? 1.f : mn;
+            __syncthreads();
+        } else {
+            // count, then 4 x 8-bit radix select of the element of ascending rank (n - 1) / 2
+            if (threadIdx.x == 0) { sel_prefix = 0u; sel_rank = 0u; }
+            uint32_t mask_bits = 0u;
+            bool empty = false;
+            for (int pass = -1; pass < 4; ++pass) {
+                hist[threadIdx.x] = 0u;     // kAssignThreads == 256
+                __syncthreads();
+                const uint32_t prefix = sel_prefix;
+                const int shift = pass < 0 ? 0 : 24 - 8 * pass;
+                for (int e = beg + threadIdx.x; e < end; e += blockDim.x) {
+                    const int pix = p.pixlist[e];
+                    if (!pixel_selected(p, pix, inf) || p.own_cls[pix] != c) continue;
+                    if (pass < 0) { atomicAdd(&hist[0], 1u); continue; }
+                    const uint32_t key = mas::ordered_bits(p.own_sim[pix]);
+                    if ((key & mask_bits) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                if (pass < 0) {
+                    const unsigned int n = hist[0];
+                    empty = n == 0u;
+                    if (threadIdx.x == 0) sel_rank = n ? (n - 1u) / 2u : 0u;
+                } else if (threadIdx.x == 0) {
+                    unsigned int rank = sel_rank, bin = 0u;
+                    for (; bin < 255u; ++bin) {
+                        if (rank < hist[bin]) break;
+                        rank -= hist[bin];
+                    }
+                    sel_rank = rank;
+                    sel_prefix = prefix | (bin << shift);
+                }
+                __syncthreads();
+                if (empty) break;
+                if (pass >= 0) mask_bits |= 0xffu << shift;
+            }
+            result = empty ? 1.f : ordered_to_float(sel_prefix);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) p.thr[(size_t)s * p.C + c] = result;
+    }
+}
+
+// one CTA per superpixel t: its UNSELECTED pixels take the label offered by the largest adjacent selected superpixel
+// (t itself included) whose test "some threshold < similarity" passes
+__global__ void __launch_bounds__(kAssignThreads) proto_propagate_kernel(LabelParams p) {
+    extern __shared__ float sproto[];          // [kGroup][F]
+    __shared__ int scls[kGroup];
+    const int t = blockIdx.x;
+    const int beg = p.offset[t], end = p.offset[t + 1];
+    if (beg == end) return;
+    const uint32_t* row = p.adj + (size_t)t * p.words;
+    // any selected neighbour at all?
+    bool any = false;
+    for (int w = 0; w < p.words && !any; ++w) any = ((row[w] | ((w == (t >> 5)) ? (1u << (t & 31)) : 0u)) & p.svalid[w]) != 0u;
+    if (!any) return;
+    const uint32_t inf_t = p.info[t];
+
+    for (int base = beg; base < end; base += blockDim.x) {
+        const int e = base + threadIdx.x;
+        const int pix = e < end ? p.pixlist[e] : -1;
+        bool done = pix < 0 || pixel_selected(p, pix, inf_t);   // selected pixels keep their own label
+        for (int w = p.words - 1; w >= 0; --w) {
+            uint32_t m = (row[w] | ((w == (t >> 5)) ? (1u << (t & 31)) : 0u)) & p.svalid[w];
+            while (m) {
+                const int bitpos = 31 - __clz(m);
+                m &= ~(1u << bitpos);
+                const int s = w * 32 + bitpos;
+                if (__syncthreads_and(done)) { m = 0u; w = 0; break; }
+                const uint32_t bits = p.info[s] & ~kGroupBit;
+                const int K = __popc(bits);
+                float best = -INFINITY;
+                int bestc = 255;
+                bool pass = false;
+                for (int k0 = 0; k0 < K; k0 += kGroup) {
+                    stage_protos(p, sproto, s, bits, k0, scls);
+                    if (!done) {
+                        float acc[kGroup];
+                        dot_group(p, sproto, pix, acc);
+#pragma unroll
+                        for (int g = 0; g < kGroup; ++g) {
+                            if (scls[g] < 0) continue;
+                            if (acc[g] > best || bestc == 255) { best = acc[g]; bestc = scls[g]; }
+                            pass |= p.thr[(size_t)s * p.C + scls[g]] < acc[g];
+                        }
+                    }
+                    __syncthreads();
+                }
+                if (!done && pass) {
+                    p.labels[pix] = (uint8_t)bestc;
+                    done = true;
+                }
+            }
+        }
+    }
+}
+
+__global__ void labeller_status_kernel(const double* acc, int only_multihot, int32_t* status) {
+    status[0] = only_multihot ? 0 : (int32_t)acc[5];   // selected pixels whose superpixel has no candidate class
+}
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Workspace {
+    uint32_t* info; unsigned long long* gmax; double* acc; int* count; int* offset; int* cursor; int* pixlist;
+    float* proto; float* own_sim; uint8_t* own_cls; float* thr; uint32_t* adj; uint32_t* svalid;
+    size_t bytes;
+};
+
+Workspace carve(void* base, int F, int C, int H, int W, int S) {
+    const size_t P = (size_t)H * W;
+    const size_t words = ((size_t)S + 31) / 32;
+    char* p = reinterpret_cast<char*>(base);
+    size_t off = 0;
+    Workspace w;
+    auto take = [&](size_t bytes) { char* q = p ? p + off : nullptr; off += align_up(bytes); return q; };
+    // zero-initialised block first (one memset): gmax, acc, count, adj, svalid
+    w.gmax = reinterpret_cast<unsigned long long*>(take((size_t)S * C * 8));
+    w.acc = reinterpret_cast<double*>(take(8 * sizeof(double)));
+    w.count = reinterpret_cast<int*>(take((size_t)S * 4));
+    w.adj = reinterpret_cast<uint32_t*>(take((size_t)S * words * 4));
+    w.svalid = reinterpret_cast<uint32_t*>(take(words * 4));
+    const size_t zeroed = off;
+    w.info = reinterpret_cast<uint32_t*>(take((size_t)S * 4));
+    w.offset = reinterpret_cast<int*>(take(((size_t)S + 1) * 4));
+    w.cursor = reinterpret_cast<int*>(take((size_t)S * 4));
+    w.pixlist = reinterpret_cast<int*>(take(P * 4));
+    w.proto = reinterpret_cast<float*>(take((size_t)S * C * F * 4));
+    w.own_sim = reinterpret_cast<float*>(take(P * 4));
+    w.own_cls = reinterpret_cast<uint8_t*>(take(P));
+    w.thr = reinterpret_cast<float*>(take((size_t)S * C * 4));
+    w.bytes = off;
+    (void)zeroed;
+    return w;
+}
+
+size_t zeroed_bytes(int C, int S) {
+    const size_t words = ((size_t)S + 31) / 32;
+    return align_up((size_t)S * C * 8) + align_up(8 * sizeof(double)) + align_up((size_t)S * 4) + align_up((size_t)S * words * 4) +
+           align_up(words * 4);
+}
+
+template <typename IdT>
+int run_labeller(const LabelParams& p, const Workspace& w, cudaStream_t st) {
+    const int threads = 256;
+    const unsigned grid_px = (unsigned)std::min<long long>(((long long)p.P + threads - 1) / threads, (long long)mas::sm_count() * 16);
+    spx_count_kernel<IdT><<<grid_px, threads, 0, st>>>(p.ids, p.P, p.S, w.count);
+    spx_scan_kernel<<<1, 1024, 0, st>>>(w.count, p.S, w.offset, w.cursor);
+    spx_fill_kernel<IdT><<<grid_px, threads, 0, st>>>(p.ids, p.P, p.S, w.offset, w.cursor, w.pixlist);
+    spx_adjacency_kernel<IdT><<<grid_px, threads, 0, st>>>(p.ids, p.H, p.W, p.S, p.words, w.adj);
+    const long long entries = (long long)p.S * p.C;
+    proto_gather_kernel<<<(unsigned)((entries * 32 + threads - 1) / threads), threads, 0, st>>>(p);
+    const size_t smem = (size_t)kGroup * p.F * sizeof(float);
+    proto_assign_kernel<<<p.S, kAssignThreads, smem, st>>>(p);
+    proto_propagate_kernel<<<p.S, kAssignThreads, smem, st>>>(p);
+    mas::count_launches(7);
+    MAS_LAUNCH_OK("prototype labeller kernels");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int mas_candidate_argmax_dev(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask,
+                                        const uint32_t* info, int n_img, int channels, int height, int width, int nseg,
+                                        uint8_t* labels, void* stream) {
+    MAS_REQUIRE(logits && ids && mask && info && labels, MAS_E_BADARG, "candidate_argmax: null pointer");
+    MAS_REQUIRE(n_img >= 0 && height > 0 && width > 0 && nseg > 0, MAS_E_BADARG, "candidate_argmax: bad shape");
+    MAS_REQUIRE(channels >= 1 && channels <= MAS_MAX_LOSS_CLASSES, MAS_E_RANGE, "candidate_argmax: channels out of range");
+    MAS_REQUIRE(ids_dtype == MAS_I32 || ids_dtype == MAS_I64, MAS_E_BADARG, "candidate_argmax: bad ids dtype");
+    if (n_img == 0) return 0;
+    const long long P = (long long)height * width;
+    MAS_REQUIRE(P < (1ll << 31), MAS_E_RANGE, "candidate_argmax: image too large");
+    const long long n_pix = P * n_img;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)std::min<long long>((n_pix + threads - 1) / threads, (long long)mas::sm_count() * 16);
+    if (ids_dtype == MAS_I64)
+        candidate_argmax_kernel<long long><<<blocks, threads, 0, (cudaStream_t)stream>>>(logits, ids, mask, info, n_pix, (int)P, channels, nseg, labels);
+    else
+        candidate_argmax_kernel<int32_t><<<blocks, threads, 0, (cudaStream_t)stream>>>(logits, ids, mask, info, n_pix, (int)P, channels, nseg, labels);
+    mas::count_launches(1);
+    MAS_LAUNCH_OK("candidate_argmax_kernel");
+    return 0;
+}
+
+extern "C" size_t mas_proto_labeller_workspace_bytes(int feat_channels, int channels, int height, int width, int nseg) {
+    if (feat_channels <= 0 || channels <= 0 || height <= 0 || width <= 0 || nseg <= 0) return 0;
+    return carve(nullptr, feat_channels, channels, height, width, nseg).bytes;
+}
+
+extern "C" int mas_proto_labeller_dev(const float* feats, int feat_channels, const float* logits, int channels,
+                                      const uint8_t* targets, int target_channels, const uint8_t* mask, const void* ids,
+                                      int ids_dtype, int height, int width, int nseg, int only_multihot, int threshold_mode,
+                                      uint8_t* labels, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+    MAS_REQUIRE(feats && logits && targets && mask && ids && labels && status && workspace, MAS_E_BADARG, "proto_labeller: null pointer");
+    MAS_REQUIRE(feat_channels > 0 && height > 0 && width > 0 && nseg > 0, MAS_E_BADARG, "proto_labeller: bad shape");
+    MAS_REQUIRE(channels >= 2 && channels <= MAS_MAX_LOSS_CLASSES && channels <= target_channels, MAS_E_RANGE,
+                "proto_labeller: channels=%d must be in [2,%d] and <= target_channels", channels, MAS_MAX_LOSS_CLASSES);
+    MAS_REQUIRE(ids_dtype == MAS_I32 || ids_dtype == MAS_I64, MAS_E_BADARG, "proto_labeller: bad ids dtype");
+    MAS_REQUIRE(threshold_mode == MAS_THRESHOLD_MEDIAN || threshold_mode == MAS_THRESHOLD_MIN, MAS_E_BADARG, "proto_labeller: bad threshold mode");
+    MAS_REQUIRE((long long)height * width < (1ll << 31), MAS_E_RANGE, "proto_labeller: image too large");
+    MAS_REQUIRE((size_t)kGroup * feat_channels * sizeof(float) <= 48 * 1024, MAS_E_RANGE, "proto_labeller: feat_channels too large");
+    MAS_REQUIRE(((uintptr_t)workspace) % 256 == 0, MAS_E_BADARG, "proto_labeller: workspace must be 256-byte aligned");
+    const Workspace w = carve(workspace, feat_channels, channels, height, width, nseg);
+    MAS_REQUIRE(workspace_bytes >= w.bytes, MAS_E_WORKSPACE, "proto_labeller: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long P = (long long)height * width;
+
+    MAS_CUDA_OK(cudaMemsetAsync(workspace, 0, zeroed_bytes(channels, nseg), st));
+    MAS_CUDA_OK(cudaMemsetAsync(labels, 0xFF, (size_t)P, st));
+    // candidate words; arg-max-probability pixel per (superpixel, candidate class): softmax with T = 1 (:140)
+    int rc = mas_multihot_info_dev(targets, nseg, target_channels, channels, only_multihot ? MAS_GROUP_ONLYMULTI : MAS_GROUP_ALL,
+                                   w.info, stream);
+    if (rc != 0) return rc;
+    rc = mas_multihot_loss_fwd_dev(logits, ids, ids_dtype, mask, w.info, 1, channels, height, width, nseg, 1.0f,
+                                   MAS_LOSS_CHOICE | MAS_LOSS_GROUP, w.acc, reinterpret_cast<uint64_t*>(w.gmax), stream);
+    if (rc != 0) return rc;
+    labeller_status_kernel<<<1, 1, 0, st>>>(w.acc, only_multihot, status);
+    mas::count_launches(1);
+
+    LabelParams p = {};
+    p.feats = feats; p.mask = mask; p.ids = ids;
+    p.F = feat_channels; p.C = channels; p.H = height; p.W = width; p.S = nseg; p.P = (int)P;
+    p.threshold_min = threshold_mode == MAS_THRESHOLD_MIN;
+    p.info = w.info; p.gmax = w.gmax; p.offset = w.offset; p.pixlist = w.pixlist; p.proto = w.proto;
+    p.own_sim = w.own_sim; p.own_cls = w.own_cls; p.thr = w.thr; p.adj = w.adj; p.svalid = w.svalid;
+    p.words = (nseg + 31) / 32;
+    p.labels = labels;
+    return ids_dtype == MAS_I64 ? run_labeller<long long>(p, w, st) : run_labeller<int32_t>(p, w, st);
+}

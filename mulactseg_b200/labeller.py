@@ -1,0 +1,72 @@
+"""Drop-in stage-2 pseudo-label generation (same signatures as the reference's ``ActiveTrainer`` methods).
+
+Reference (file:line relative to the reference checkout):
+  ``pseudo_label_generation(labels, feats, inputs, targets, spmasks, superpixels) -> LongTensor (N,H,W)``
+      trainer/eval_save_cosplbl_prop.py:121-314                (``only_multihot=True``)
+      trainer/eval_save_cosplbl_prop_includeonehot.py:121-316  (``only_multihot=False``; the shipped recipe)
+  ``top_pseudo_label_generation(labels, inputs, targets, spmasks, superpixels)``
+      trainer/eval_within_multihot.py:93-146
+``ProtoLabellerMixin`` / ``TopLabellerMixin`` give a trainer class these methods with the reference's argument
+lists; ``args.cosprop_threshold_method`` ('median' | 'min') and ``args.nseg`` are read like the reference does.
+The VOC multi-scale variant (``..._includeonehot_voc_ms.py``) is out of scope this round.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, ops
+
+
+def _prep(targets, spmasks, superpixels):
+    trg = (targets if targets.dtype == torch.uint8 else targets.to(torch.uint8)).contiguous()
+    mask = (spmasks if spmasks.dtype in (torch.bool, torch.uint8) else spmasks.bool()).contiguous()
+    spx = (superpixels if superpixels.dtype in (torch.int32, torch.int64) else superpixels.long()).contiguous()
+    return trg, mask, spx
+
+
+def pseudo_label_generation(labels, feats, inputs, targets, spmasks, superpixels, only_multihot: bool = False,
+                            threshold: str = "median", check: bool = True) -> torch.Tensor:
+    """(N,H,W) int64 pseudo labels, 255 = unlabeled.  ``labels`` is only used for its shape, as in the reference.
+    ``check`` (one sync per call, the caller reads the result back anyway): raise like the reference (:226) when a
+    selected superpixel has no candidate class."""
+    if not feats.is_cuda:
+        raise RuntimeError("mulactseg_b200 labellers need CUDA tensors (there is no CPU path)")
+    n = inputs.shape[0]
+    trg, mask, spx = _prep(targets, spmasks, superpixels)
+    feats = feats.contiguous().float()
+    inputs = inputs.contiguous().float()
+    outs, stats = [], []
+    for i in range(n):
+        lab, status = ops.proto_labeller(feats[i], inputs[i], trg[i], mask[i], spx[i], only_multihot, threshold)
+        outs.append(lab)
+        stats.append(status)
+    out = torch.stack(outs).long()
+    if check:
+        bad = int(torch.cat(stats).sum())
+        if bad:
+            raise RuntimeError(f"{bad} selected pixels belong to superpixels without any candidate class "
+                               "(the reference fails on such input, eval_save_cosplbl_prop.py:226)")
+    return out
+
+
+def top_pseudo_label_generation(labels, inputs, targets, spmasks, superpixels) -> torch.Tensor:
+    """eval_within_multihot.py:93-146: arg-max of (logit * multi-hot row) on selected pixels, 255 elsewhere."""
+    if not inputs.is_cuda:
+        raise RuntimeError("mulactseg_b200 labellers need CUDA tensors (there is no CPU path)")
+    trg, mask, spx = _prep(targets, spmasks, superpixels)
+    info = ops.multihot_info(trg, inputs.shape[1], _lib.MAS_GROUP_ALL)
+    return ops.candidate_argmax(inputs.contiguous().float(), spx, mask, info, trg.shape[1]).long()
+
+
+class ProtoLabellerMixin:
+    """``ActiveTrainer.pseudo_label_generation`` of eval_save_cosplbl_prop*.py for a trainer with ``self.args``."""
+    only_multihot = False
+
+    def pseudo_label_generation(self, labels, feats, inputs, targets, spmasks, superpixels):
+        return pseudo_label_generation(labels, feats, inputs, targets, spmasks, superpixels, self.only_multihot,
+                                       getattr(self.args, "cosprop_threshold_method", "median"))
+
+
+class TopLabellerMixin:
+    def top_pseudo_label_generation(self, labels, inputs, targets, spmasks, superpixels):
+        return top_pseudo_label_generation(labels, inputs, targets, spmasks, superpixels)

@@ -1,0 +1,229 @@
+"""Drop-in stage-1 losses (same class names, constructors and ``forward`` signatures as the reference's
+``nn.Module``s), computed by the fused sm_100a kernels of ``csrc/losses.cu``.
+
+Reference classes mirrored (file:line relative to the reference checkout):
+  ``GroupMultiLabelCE``            utils/loss.py:81-141            (targets[..., :-1]; net without ignore channel)
+  ``GroupMultiLabelCE_``           trainer/active_joint_multi_predignore.py:74-128
+  ``GroupMultiLabelCE_onlymulti``  trainer/active_joint_multi_predignore_mclossablation2.py:17-79
+  ``MultiChoiceCE``                utils/loss.py:535-588           (targets[..., :-1], empty rows dropped)
+  ``MultiChoiceCE_``               trainer/active_joint_multi_predignore.py:17-73
+  ``OnehotCEMultihotChoice``       trainer/active_joint_multi_predignore_lossdecomp.py:16-72  (``strict_multihot=False``)
+  ``OnehotCEMultihotChoiceVOC``    trainer/active_joint_multi_lossdecomp.py:17-74             (multi-hot := row-sum > 1)
+``forward(inputs (N,C',H,W) f32, targets (N,S,Ct) u8, superpixels (N,H,W) i64|i32, spmasks (N,H,W) bool)``.
+
+All of them are one autograd function, ``segmented_loss_sums``: one pass over the logits of the masked
+pixels yields the four bucket sums / counts (one-hot, multi-hot, empty-row, group) and the packed
+max-pool table; ``backward`` is one pass writing the dense gradient.  Modules that are called on the same
+``inputs`` one after the other (the trainer computes the group loss and the decomposed loss back to back,
+``..._lossdecomp.py:101-104``) share a single pass when their temperatures agree -- see ``SharedPass``.
+There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib, ops
+
+
+class _SegmentedLossSums(torch.autograd.Function):
+    """sums (4,) f32 = [one-hot, multi-hot, empty-row, group] bucket sums (differentiable w.r.t. inputs);
+    counts (4,) f64 (not differentiable)."""
+
+    @staticmethod
+    def forward(ctx, inputs, spx, mask, info, nseg, temperature, flags):
+        x = inputs.contiguous()
+        acc, gmax = ops.multihot_loss_forward(x, spx, mask, info, nseg, temperature, flags)
+        ctx.save_for_backward(x, spx, mask, info, gmax if gmax is not None else torch.empty(0, device=x.device))
+        ctx.nseg, ctx.temperature, ctx.flags = nseg, temperature, flags
+        sums = acc[0::2].to(torch.float32)
+        counts = acc[1::2].clone()
+        ctx.mark_non_differentiable(counts)
+        return sums, counts
+
+    @staticmethod
+    def backward(ctx, grad_sums, _grad_counts):
+        x, spx, mask, info, gmax = ctx.saved_tensors
+        coef = grad_sums.to(torch.float32).contiguous()
+        grad = ops.multihot_loss_backward(x, spx, mask, info, gmax if gmax.numel() else None, coef, ctx.nseg,
+                                          ctx.temperature, ctx.flags)
+        return grad, None, None, None, None, None, None
+
+
+def _prepare(inputs, targets, superpixels, spmasks):
+    if not inputs.is_cuda:
+        raise RuntimeError("mulactseg_b200 losses need CUDA tensors (there is no CPU path)")
+    n, c = inputs.shape[:2]
+    if c > _lib.MAS_MAX_LOSS_CLASSES:
+        raise RuntimeError(f"at most {_lib.MAS_MAX_LOSS_CLASSES} channels are supported, got {c}")
+    trg = targets if targets.dtype == torch.uint8 else targets.to(torch.uint8)
+    spx = superpixels if superpixels.dtype in (torch.int32, torch.int64) else superpixels.long()
+    mask = spmasks if spmasks.dtype in (torch.bool, torch.uint8) else spmasks.bool()
+    return trg.contiguous(), spx.contiguous(), mask.contiguous()
+
+
+def segmented_loss_sums(inputs, targets, superpixels, spmasks, temperature: float, group_mode: Optional[int],
+                        want_choice: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One fused pass.  ``group_mode``: None (no group loss), MAS_GROUP_ALL or MAS_GROUP_ONLYMULTI.
+    The candidate sets are the first ``inputs.shape[1]`` target channels (== ``targets[..., :C']``)."""
+    trg, spx, mask = _prepare(inputs, targets, superpixels, spmasks)
+    nseg = trg.shape[1]
+    info = ops.multihot_info(trg, inputs.shape[1], _lib.MAS_GROUP_ALL if group_mode is None else group_mode)
+    flags = (_lib.MAS_LOSS_CHOICE if want_choice else 0) | (_lib.MAS_LOSS_GROUP if group_mode is not None else 0)
+    return _SegmentedLossSums.apply(inputs, spx, mask, info, nseg, float(temperature), flags)
+
+
+class SharedPass:
+    """Lets several loss modules called on the SAME tensors in a row reuse one fused pass.
+
+    The first module asks for everything any member needs (group mode + choice buckets); members called
+    next with identical arguments (same tensor objects and versions, same temperature) get the cached
+    sums.  Anything else falls back to its own pass, so results never depend on the sharing."""
+
+    def __init__(self):
+        self._key = None
+        self._value = None
+        self.members = []
+
+    def register(self, module):
+        self.members.append(weakref.ref(module))
+
+    def _wanted(self, temperature):
+        group_mode, choice = None, False
+        for ref in self.members:
+            m = ref()
+            if m is None or float(m.temp) != float(temperature):
+                continue
+            if m.group_mode is not None:
+                if group_mode is not None and group_mode != m.group_mode:
+                    return None
+                group_mode = m.group_mode
+            choice = choice or m.wants_choice
+        return group_mode, choice
+
+    def sums(self, module, inputs, targets, superpixels, spmasks):
+        key = (id(inputs), inputs._version, id(targets), targets._version, id(superpixels), id(spmasks), float(module.temp),
+               inputs.shape[1], targets.shape[-1])
+        if self._key == key and self._value is not None:
+            gm, choice, value = self._value
+            if (module.group_mode is None or module.group_mode == gm) and (choice or not module.wants_choice):
+                return value
+        wanted = self._wanted(module.temp)
+        if wanted is None:
+            wanted = (module.group_mode, module.wants_choice)
+        value = segmented_loss_sums(inputs, targets, superpixels, spmasks, module.temp, wanted[0], wanted[1])
+        self._key, self._value = key, (wanted[0], wanted[1], value)
+        return value
+
+
+class _SegmentedLoss(nn.Module):
+    group_mode: Optional[int] = None
+    wants_choice = False
+
+    def __init__(self, temperature=1.0, reduction="mean"):
+        super().__init__()
+        self.eps = 1e-8
+        self.temp = temperature
+        self.reduction = reduction
+        self.shared: Optional[SharedPass] = None
+
+    def share(self, shared: SharedPass):
+        self.shared = shared
+        shared.register(self)
+        return self
+
+    def _sums(self, inputs, targets, superpixels, spmasks):
+        if self.shared is not None:
+            return self.shared.sums(self, inputs, targets, superpixels, spmasks)
+        return segmented_loss_sums(inputs, targets, superpixels, spmasks, self.temp, self.group_mode, self.wants_choice)
+
+
+class GroupMultiLabelCE(_SegmentedLoss):
+    """utils/loss.py:81-141.  The net has ``targets.shape[-1] - 1`` channels; candidates = targets[..., :-1]."""
+    group_mode = _lib.MAS_GROUP_ALL
+
+    def __init__(self, args, num_class, num_superpixel, temperature=1.0, reduction="mean"):
+        super().__init__(temperature, reduction)
+        self.args = args
+        self.num_class = num_class
+        self.num_superpixel = num_superpixel
+
+    def forward(self, inputs, targets, superpixels, spmasks):
+        sums, counts = self._sums(inputs, targets, superpixels, spmasks)
+        num_valid = 1 + counts[3]
+        if self.reduction == "mean":
+            return sums[3] / num_valid.to(torch.float32)
+        if self.reduction == "none":
+            return sums[3], num_valid
+        raise NotImplementedError
+
+
+class GroupMultiLabelCE_(GroupMultiLabelCE):
+    """trainer/active_joint_multi_predignore.py:74-128 (targets not sliced: the net predicts the ignore channel)."""
+
+
+class GroupMultiLabelCE_onlymulti(GroupMultiLabelCE_):
+    """trainer/active_joint_multi_predignore_mclossablation2.py:17-79: only pixels of multi-hot superpixels."""
+    group_mode = _lib.MAS_GROUP_ONLYMULTI
+
+
+class MultiChoiceCE(_SegmentedLoss):
+    """utils/loss.py:535-588: -log of the candidate-set probability mass over labelled masked pixels."""
+    wants_choice = True
+
+    def __init__(self, num_class, temperature=1.0, reduction="mean"):
+        super().__init__(temperature, reduction)
+        self.num_class = num_class
+
+    def forward(self, inputs, targets, superpixels, spmasks):
+        if self.reduction != "mean":
+            raise NotImplementedError("only reduction='mean' (what the shipped recipes use) is provided")
+        sums, counts = self._sums(inputs, targets, superpixels, spmasks)
+        return (sums[0] + sums[1]) / (1 + counts[0] + counts[1]).to(torch.float32)
+
+
+class MultiChoiceCE_(MultiChoiceCE):
+    """trainer/active_joint_multi_predignore.py:17-73."""
+
+
+class OnehotCEMultihotChoice(MultiChoiceCE):
+    """trainer/active_joint_multi_predignore_lossdecomp.py:16-72 -> (one-hot CE, multi-hot multi-choice).
+
+    The reference defines multi-hot := not one-hot and asserts that this equals row-sum > 1 (:65-67), i.e. it
+    raises on a selected pixel whose superpixel has no candidate class.  ``assert_partition=True`` (default)
+    keeps that check (one device sync, as in the reference); False skips it and counts such pixels in the
+    multi-hot bucket like the reference's arithmetic would."""
+    strict_multihot = False
+
+    def __init__(self, num_class, temperature=1.0, reduction="mean", assert_partition=True):
+        super().__init__(num_class, temperature, reduction)
+        assert self.reduction == "mean"
+        self.assert_partition = assert_partition
+
+    def forward(self, inputs, targets, superpixels, spmasks):
+        sums, counts = self._sums(inputs, targets, superpixels, spmasks)
+        one = sums[0] / (1 + counts[0]).to(torch.float32)
+        if self.strict_multihot:
+            return one, sums[1] / (1 + counts[1]).to(torch.float32)
+        if self.assert_partition:
+            assert float(counts[2]) == 0.0   # ..._lossdecomp.py:67
+        return one, (sums[1] + sums[2]) / (1 + counts[1] + counts[2]).to(torch.float32)
+
+
+class OnehotCEMultihotChoiceVOC(OnehotCEMultihotChoice):
+    """trainer/active_joint_multi_lossdecomp.py:17-74 (multi-hot := row-sum > 1, no assertion)."""
+    strict_multihot = True
+
+
+def stage1_criterion(args, num_classes: int, voc: bool = False):
+    """The two criteria ``ActiveTrainer.get_criterion`` installs (``..._lossdecomp.py:78-81``), wired to share
+    one fused pass per step when ``group_ce_temp == multi_ce_temp``."""
+    shared = SharedPass()
+    group = GroupMultiLabelCE_onlymulti(args=args, num_class=num_classes, num_superpixel=args.nseg,
+                                        temperature=args.group_ce_temp).share(shared)
+    cls = OnehotCEMultihotChoiceVOC if voc else OnehotCEMultihotChoice
+    multi = cls(num_class=num_classes, temperature=args.multi_ce_temp).share(shared)
+    return group, multi

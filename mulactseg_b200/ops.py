@@ -161,3 +161,116 @@ def topk_keys(keys: torch.Tensor, k: int, sort: bool = True) -> Tuple[torch.Tens
         if sort and k > 1:
             _lib.call("mas_sort_desc_u64_dev", out.data_ptr(), k, _stream(keys))
     return out, count
+
+
+# ------------------------------------------------------------------------------------------------ stage-1 losses
+def _ids_dtype(spx: torch.Tensor) -> int:
+    if spx.dtype == torch.int64:
+        return _lib.MAS_I64
+    if spx.dtype == torch.int32:
+        return _lib.MAS_I32
+    raise RuntimeError(f"superpixels: expected int32 or int64, got {spx.dtype}")
+
+
+def multihot_info(targets: torch.Tensor, channels: int, group_mode: int) -> torch.Tensor:
+    """(..., Ct) uint8 multi-hot targets -> (...) candidate words (int32 storage, see ``mas_multihot_info_dev``)."""
+    _want(targets, "targets", torch.uint8)
+    ct = targets.shape[-1]
+    info = torch.empty(targets.shape[:-1], dtype=torch.int32, device=targets.device)
+    with torch.cuda.device(targets.device):
+        _lib.call("mas_multihot_info_dev", targets.data_ptr(), info.numel(), int(ct), int(channels), int(group_mode),
+                  info.data_ptr(), _stream(targets))
+    return info
+
+
+def _loss_args(logits, spx, mask, info, nseg):
+    _want(logits, "inputs", torch.float32, 4)
+    _want(spx, "superpixels", (torch.int32, torch.int64), 3)
+    _want(mask, "spmasks", (torch.bool, torch.uint8), 3)
+    _want(info, "info", torch.int32, 2)
+    n, c, h, w = logits.shape
+    if tuple(spx.shape) != (n, h, w) or tuple(mask.shape) != (n, h, w):
+        raise RuntimeError(f"superpixels {tuple(spx.shape)} / spmasks {tuple(mask.shape)} do not match inputs {tuple(logits.shape)}")
+    if tuple(info.shape) != (n, nseg):
+        raise RuntimeError(f"targets: expected {(n, nseg)} regions, got {tuple(info.shape)}")
+    return n, c, h, w
+
+
+def multihot_loss_forward(logits: torch.Tensor, spx: torch.Tensor, mask: torch.Tensor, info: torch.Tensor, nseg: int,
+                          temperature: float, flags: int):
+    """-> (acc (8,) f64 bucket sums / counts, group_max (N,nseg,C) i64 packed maxima or None)."""
+    n, c, h, w = _loss_args(logits, spx, mask, info, nseg)
+    acc = torch.zeros(8, dtype=torch.float64, device=logits.device)
+    gmax = torch.zeros((n, nseg, c), dtype=torch.int64, device=logits.device) if flags & _lib.MAS_LOSS_GROUP else None
+    with torch.cuda.device(logits.device):
+        _lib.call("mas_multihot_loss_fwd_dev", logits.data_ptr(), spx.data_ptr(), _ids_dtype(spx), mask.data_ptr(),
+                  info.data_ptr(), n, c, h, w, int(nseg), float(temperature), int(flags), acc.data_ptr(), _ptr(gmax),
+                  _stream(logits))
+    return acc, gmax
+
+
+def multihot_loss_backward(logits: torch.Tensor, spx: torch.Tensor, mask: torch.Tensor, info: torch.Tensor,
+                           gmax: Optional[torch.Tensor], coef: torch.Tensor, nseg: int, temperature: float,
+                           flags: int) -> torch.Tensor:
+    """Dense d(sum_k coef[k] * bucket_sum[k]) / d logits; coef = 4 device floats."""
+    n, c, h, w = _loss_args(logits, spx, mask, info, nseg)
+    _want(coef, "coef", torch.float32, 1)
+    if coef.numel() != 4:
+        raise RuntimeError("coef must hold 4 floats")
+    grad = torch.empty_like(logits)
+    with torch.cuda.device(logits.device):
+        _lib.call("mas_multihot_loss_bwd_dev", logits.data_ptr(), spx.data_ptr(), _ids_dtype(spx), mask.data_ptr(),
+                  info.data_ptr(), _ptr(gmax), coef.data_ptr(), n, c, h, w, int(nseg), float(temperature), int(flags),
+                  grad.data_ptr(), _stream(logits))
+    return grad
+
+
+# ------------------------------------------------------------------------------------------------ stage-2 labellers
+def candidate_argmax(logits: torch.Tensor, spx: torch.Tensor, mask: torch.Tensor, info: torch.Tensor, nseg: int) -> torch.Tensor:
+    """(N,H,W) uint8 labels: arg-max of logit * multi-hot row on selected pixels, 255 elsewhere."""
+    n, c, h, w = _loss_args(logits, spx, mask, info, nseg)
+    labels = torch.empty((n, h, w), dtype=torch.uint8, device=logits.device)
+    with torch.cuda.device(logits.device):
+        _lib.call("mas_candidate_argmax_dev", logits.data_ptr(), spx.data_ptr(), _ids_dtype(spx), mask.data_ptr(),
+                  info.data_ptr(), n, c, h, w, int(nseg), labels.data_ptr(), _stream(logits))
+    return labels
+
+
+_workspaces = {}
+
+
+def _labeller_workspace(device, fch, c, h, w, nseg) -> torch.Tensor:
+    need = int(_lib.load().mas_proto_labeller_workspace_bytes(fch, c, h, w, nseg))
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.uint8, device=device)   # caching-allocator blocks are >= 512-byte aligned
+        _workspaces[key] = buf
+    return buf
+
+
+def proto_labeller(feats: torch.Tensor, logits: torch.Tensor, targets: torch.Tensor, mask: torch.Tensor, spx: torch.Tensor,
+                   only_multihot: bool, threshold: str):
+    """One image: feats (F,H,W) f32, logits (C,H,W) f32, targets (S,Ct) u8, mask (H,W) bool, spx (H,W) i32|i64
+    -> (labels (H,W) uint8, status (1,) int32 on the device).  See ``mas_proto_labeller_dev``."""
+    _want(feats, "feats", torch.float32, 3)
+    _want(logits, "inputs", torch.float32, 3)
+    _want(targets, "targets", torch.uint8, 2)
+    _want(mask, "spmasks", (torch.bool, torch.uint8), 2)
+    _want(spx, "superpixels", (torch.int32, torch.int64), 2)
+    fch, h, w = feats.shape
+    c = logits.shape[0]
+    nseg, ct = targets.shape
+    if tuple(logits.shape[1:]) != (h, w) or tuple(mask.shape) != (h, w) or tuple(spx.shape) != (h, w):
+        raise RuntimeError("feats / inputs / spmasks / superpixels spatial shapes differ")
+    if threshold not in ("median", "min"):
+        raise NotImplementedError(f"cosprop_threshold_method={threshold!r}")
+    labels = torch.empty((h, w), dtype=torch.uint8, device=feats.device)
+    status = torch.zeros(1, dtype=torch.int32, device=feats.device)
+    ws = _labeller_workspace(feats.device, fch, c, h, w, nseg)
+    with torch.cuda.device(feats.device):
+        _lib.call("mas_proto_labeller_dev", feats.data_ptr(), fch, logits.data_ptr(), c, targets.data_ptr(), ct,
+                  mask.data_ptr(), spx.data_ptr(), _ids_dtype(spx), h, w, nseg, int(bool(only_multihot)),
+                  _lib.MAS_THRESHOLD_MEDIAN if threshold == "median" else _lib.MAS_THRESHOLD_MIN,
+                  labels.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), _stream(feats))
+    return labels, status

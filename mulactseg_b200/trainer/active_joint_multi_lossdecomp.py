@@ -1,0 +1,8 @@
+"""Hot-path part of the reference's ``trainer/active_joint_multi_lossdecomp.py`` (VOC recipe): ``get_criterion``
+(:80-83) with the fused criteria."""
+from ..losses import GroupMultiLabelCE_onlymulti, OnehotCEMultihotChoiceVOC as OnehotCEMultihotChoice, stage1_criterion  # noqa: F401
+
+
+class CriterionMixin:
+    def get_criterion(self):
+        self.group_multi_loss, self.multi_pos_loss = stage1_criterion(self.args, self.num_classes, voc=True)

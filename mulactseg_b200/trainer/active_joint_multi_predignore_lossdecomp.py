@@ -1,0 +1,8 @@
+"""Hot-path part of the reference's ``trainer/active_joint_multi_predignore_lossdecomp.py``: ``get_criterion``
+(:76-81) with the fused criteria; ``train_impl`` (:83-117) calls them unchanged."""
+from ..losses import GroupMultiLabelCE_onlymulti, OnehotCEMultihotChoice, stage1_criterion  # noqa: F401
+
+
+class CriterionMixin:
+    def get_criterion(self):
+        self.group_multi_loss, self.multi_pos_loss = stage1_criterion(self.args, self.num_classes, voc=False)
