@@ -61,6 +61,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def scorer_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the scorer, from the committed ncu --set full capture
+    of the same configuration (4 images x 19 x 1024 x 2048 f32 per launch); None if the summary is missing."""
+    path = os.path.join(ROOT, "profiles", "r1_v2_scorer_tma_c19_prob1_full.txt")
+    try:
+        with open(path) as f:
+            vals = [int(line.split()[-1]) for line in f if line.startswith("traffic = dram read + write")]
+        return int(np.mean(vals)) if vals else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -255,7 +267,7 @@ def run_ours(args):
     achieved = float(np.mean(bytes_per_img * imgs[full] / (dur[full] * 1e-3))) / 1e9
     peak, peak_src = peaks()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "bvsb_stats_kernel<19,f32,vec4,prob>", "peak_source": peak_src + ", burst",
+                "traffic": scorer_traffic(), "kernel": "bvsb_stats_tma_kernel<19,f32,prob>", "peak_source": peak_src + ", burst",
                 "bytes_per_launch": int(bytes_per_img * REF_BATCH), "mean_launch_ms": float(np.mean(dur[full])),
                 "kernel_share_of_step": float(dur.sum() / args.steps / ms_step)}
 
