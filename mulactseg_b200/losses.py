@@ -86,6 +86,7 @@ class SharedPass:
     def __init__(self):
         self._key = None
         self._value = None
+        self._refs = ()
         self.members = []
 
     def register(self, module):
@@ -105,9 +106,9 @@ class SharedPass:
         return group_mode, choice
 
     def sums(self, module, inputs, targets, superpixels, spmasks):
-        key = (id(inputs), inputs._version, id(targets), targets._version, id(superpixels), id(spmasks), float(module.temp),
-               inputs.shape[1], targets.shape[-1])
-        if self._key == key and self._value is not None:
+        tensors = (inputs, targets, superpixels, spmasks)
+        key = (tuple(t._version for t in tensors), float(module.temp), torch.is_grad_enabled(), inputs.requires_grad)
+        if self._key == key and self._value is not None and all(r() is t for r, t in zip(self._refs, tensors)):
             gm, choice, value = self._value
             if (module.group_mode is None or module.group_mode == gm) and (choice or not module.wants_choice):
                 return value
@@ -115,6 +116,8 @@ class SharedPass:
         if wanted is None:
             wanted = (module.group_mode, module.wants_choice)
         value = segmented_loss_sums(inputs, targets, superpixels, spmasks, module.temp, wanted[0], wanted[1])
+        # identity through weak references: a recycled id() of a dead tensor can never hit the cache
+        self._refs = tuple(weakref.ref(t) for t in tensors)
         self._key, self._value = key, (wanted[0], wanted[1], value)
         return value
 

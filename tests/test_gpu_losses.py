@@ -153,6 +153,34 @@ def test_shared_pass_equals_separate_passes_and_trainer_total():
     assert g2.item() == alone.item() and ce2.item() == ce.item() and mc2.item() == mc.item()
 
 
+def test_shared_pass_never_serves_stale_results():
+    from mulactseg_b200 import losses as L
+    n, c, h, w, nseg = 2, 8, 16, 32, 8
+    spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=2).to(DEV)
+    trg = synth.multihot_targets(n, nseg, c, seed=3, p_ignore=0.0).to(DEV)
+    mask = synth.region_mask(spx, nseg, 0.7, seed=4)
+    args = types.SimpleNamespace(nseg=nseg, group_ce_temp=0.1, multi_ce_temp=0.1)
+    group, multi = L.stage1_criterion(args, c - 1)
+    seen = []
+    for step in range(4):                       # fresh logits every step, like net(images) in the trainer
+        x = synth.logits(n, c, h, w, "cosine", seed=10 + step).to(DEV).requires_grad_(True)
+        with torch.no_grad():
+            g0 = group(x, trg, spx, mask)       # a no-grad evaluation must not poison the cache
+        g = group(x, trg, spx, mask)
+        ce, mc = multi(x, trg, spx, mask)
+        (ce + mc + g).backward()
+        assert x.grad is not None and g0.item() == g.item()
+        alone = L.GroupMultiLabelCE_onlymulti(args, c - 1, nseg, temperature=0.1)(x, trg, spx, mask)
+        assert alone.item() == g.item()
+        seen.append(g.item())
+        del x
+    assert len(set(seen)) == 4
+    x = synth.logits(n, c, h, w, "cosine", seed=99).to(DEV)
+    a = group(x, trg, spx, mask).item()
+    x.mul_(0.5)                                 # in-place change bumps the version: recomputed
+    assert group(x, trg, spx, mask).item() != a
+
+
 def test_empty_candidate_row_raises_like_the_reference():
     from mulactseg_b200 import losses as L
     n, c, h, w, nseg = 1, 6, 8, 16, 4

@@ -16,6 +16,7 @@ from mulactseg_b200 import labeller, losses, synth  # noqa: E402
 
 
 def time_ms(fn, warmup=3, iters=10):
+    torch.cuda.cudart().cudaProfilerStart()     # ncu --profile-from-start off skips the input generation
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -43,15 +44,18 @@ def bench_losses(res, profile):
     for rho in (0.02, 0.2, 1.0):
         mask = synth.region_mask(spx, nseg, rho, seed=4)
         group, multi = losses.stage1_criterion(args, c - 1)
-        xin = x.clone().requires_grad_(True)
+        xs = [x.clone().requires_grad_(True) for _ in range(3)]   # a fresh `preds` every step, like net(images)
+        turn = [0]
 
         def fwd():
+            turn[0] += 1
+            xin = xs[turn[0] % len(xs)]
+            xin.grad = None
             g = group(xin, trg, spx, mask)
             ce, mc = multi(xin, trg, spx, mask)
             return 16.0 * ce + 8.0 * mc + g
 
         def step():
-            xin.grad = None
             fwd().backward()
 
         with torch.no_grad():
