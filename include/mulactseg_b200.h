@@ -253,6 +253,23 @@ int mas_proto_labeller_dev(const float* feats, int feat_channels, const float* l
                            int height, int width, int nseg, int only_multihot, int threshold_mode,
                            uint8_t* labels, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ offline multi-hot label generation
+ *
+ * mas_multihot_labels_dev -- ONE image of RegionCityscapesTensor.__getitem__ (dataloader/region_cityscapes_tensor.py:33-84,
+ * driven by tools/label_assignment_tensor.py:50-67): per-superpixel class histogram of the ground-truth train-id map.
+ *   ids (H, W) int32|int64, target (H, W) uint8 train ids (255 = ignore), keep (nseg) uint8 = 1 for the ids listed in
+ *   the region dict ("preserving_labels").
+ *   multi_hot[s][c] = 1 iff class c occurs in superpixel s, multi_hot[s][num_classes] = 1 iff label 255 occurs;
+ *   size[s] = number of pixels counted; rows of ids with keep == 0 are zero with size -1.
+ *   trim_kernel_size k > 0 (--trim_multihot_boundary): pixels within the k x k dilation of the superpixel boundaries
+ *   (skimage find_boundaries mode='thick' + binary_dilation(ones(k,k))) are left out, unless that empties the superpixel.
+ * multi_hot (nseg, num_classes + 1) uint8, size (nseg) int32; workspace: mas_multihot_labels_workspace_bytes() bytes.
+ */
+size_t mas_multihot_labels_workspace_bytes(int nseg, int num_classes);
+int mas_multihot_labels_dev(const void* ids, int ids_dtype, const uint8_t* target, const uint8_t* keep,
+                            int height, int width, int nseg, int num_classes, int trim_kernel_size,
+                            uint8_t* multi_hot, int32_t* size, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,32 +8,63 @@
 
 #include <math.h>
 #include <string.h>
+#include <map>
+#include <mutex>
 #include <vector>
 
 namespace {
 
-struct DeviceBuffers {
-    std::vector<void*> ptrs;
+// Streams, events and grow-only device buffers of the host-buffer entry points, cached per device for the life of
+// the process: cudaMalloc / cudaFree of the 1.4 GB staging area cost more than the scoring itself.  One call at a
+// time per device (the mutex is held for the whole call).
+struct HostContext {
+    std::mutex lock;
     cudaStream_t copy = nullptr, compute = nullptr;
     cudaEvent_t filled[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
-    ~DeviceBuffers() {
-        for (void* p : ptrs) cudaFree(p);
+    struct Slot { void* ptr = nullptr; size_t bytes = 0; };
+    std::vector<Slot> slots;
+    size_t next = 0;
+
+    cudaError_t init() {
+        if (compute) return cudaSuccess;
+        cudaError_t e;
+        if ((e = cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking)) != cudaSuccess) return e;
         for (int i = 0; i < 2; ++i) {
-            if (filled[i]) cudaEventDestroy(filled[i]);
-            if (drained[i]) cudaEventDestroy(drained[i]);
+            if ((e = cudaEventCreateWithFlags(&filled[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming)) != cudaSuccess) return e;
         }
-        if (copy) cudaStreamDestroy(copy);
-        if (compute) cudaStreamDestroy(compute);
+        return cudaSuccess;
     }
+    void begin() { next = 0; }
+    // the i-th buffer requested in a call is the i-th slot: calls of the same shape never reallocate
     template <typename T>
     cudaError_t alloc(T** out, size_t bytes) {
-        void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
-        if (e == cudaSuccess) ptrs.push_back(p);
-        *out = reinterpret_cast<T*>(p);
-        return e;
+        if (bytes == 0) bytes = 1;
+        if (next == slots.size()) slots.push_back(Slot());
+        Slot& s = slots[next++];
+        if (s.bytes < bytes) {
+            if (s.ptr) cudaFree(s.ptr);
+            s.ptr = nullptr; s.bytes = 0;
+            cudaError_t e = cudaMalloc(&s.ptr, bytes);
+            if (e != cudaSuccess) return e;
+            s.bytes = bytes;
+        }
+        *out = reinterpret_cast<T*>(s.ptr);
+        return cudaSuccess;
     }
 };
+
+HostContext* context_for_current_device() {
+    static std::mutex table_lock;
+    static std::map<int, HostContext*> table;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> g(table_lock);
+    auto it = table.find(dev);
+    if (it == table.end()) it = table.emplace(dev, new HostContext()).first;   // lives until process exit
+    return it->second;
+}
 
 }  // namespace
 
@@ -59,16 +90,17 @@ extern "C" int mas_acquisition_host(const void* logits, int logits_dtype, const 
     const long long n_regions = (long long)n_img * nseg;
     const size_t table = (size_t)n_regions * channels;
 
-    DeviceBuffers d;
-    MAS_CUDA_OK(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
-    MAS_CUDA_OK(cudaStreamCreateWithFlags(&d.compute, cudaStreamNonBlocking));
+    HostContext* ctx = context_for_current_device();
+    MAS_REQUIRE(ctx, MAS_E_BADARG, "acquisition_host: no CUDA device");
+    std::lock_guard<std::mutex> guard(ctx->lock);
+    HostContext& d = *ctx;
+    MAS_CUDA_OK(d.init());
+    d.begin();
     char* stage_logits[2];
     int32_t* stage_ids[2];
     for (int i = 0; i < 2; ++i) {
         MAS_CUDA_OK(d.alloc(&stage_logits[i], img_logit_bytes * chunk_img));
         MAS_CUDA_OK(d.alloc(&stage_ids[i], img_id_bytes * chunk_img));
-        MAS_CUDA_OK(cudaEventCreateWithFlags(&d.filled[i], cudaEventDisableTiming));
-        MAS_CUDA_OK(cudaEventCreateWithFlags(&d.drained[i], cudaEventDisableTiming));
     }
     float *cls_sum, *d_score, *d_w = nullptr, *d_minmax = nullptr, *d_rw = nullptr;
     int32_t *cls_cnt, *d_dom = nullptr;
@@ -165,8 +197,14 @@ extern "C" int mas_select_topk_host(const float* score, const uint8_t* in_pool, 
     MAS_REQUIRE(n_img > 0 && nseg > 0 && k > 0, MAS_E_BADARG, "select_topk_host: bad size");
     const long long n = (long long)n_img * nseg;
     const long long cap = mas_sort_capacity(k);
-    DeviceBuffers d;
-    MAS_CUDA_OK(cudaStreamCreateWithFlags(&d.compute, cudaStreamNonBlocking));
+    HostContext* ctx = context_for_current_device();
+    MAS_REQUIRE(ctx, MAS_E_BADARG, "select_topk_host: no CUDA device");
+    std::lock_guard<std::mutex> guard(ctx->lock);
+    HostContext& d = *ctx;
+    MAS_CUDA_OK(d.init());
+    d.begin();
+    d.next = 16;   // slots 16.. : keeps the acquisition buffers of the same process untouched
+    while (d.slots.size() < 16) d.slots.push_back(HostContext::Slot());
     float* d_score; uint8_t* d_pool; int32_t* d_rank; uint64_t *d_keys, *d_out; int32_t* d_count; void* d_ws;
     MAS_CUDA_OK(d.alloc(&d_score, n * sizeof(float)));
     MAS_CUDA_OK(d.alloc(&d_pool, n));

@@ -274,3 +274,25 @@ def proto_labeller(feats: torch.Tensor, logits: torch.Tensor, targets: torch.Ten
                   _lib.MAS_THRESHOLD_MEDIAN if threshold == "median" else _lib.MAS_THRESHOLD_MIN,
                   labels.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), _stream(feats))
     return labels, status
+
+
+# ------------------------------------------------------------------------------------------------ offline label generation
+def multihot_labels(spx: torch.Tensor, target: torch.Tensor, keep: torch.Tensor, nseg: int, num_classes: int,
+                    trim_kernel_size: int = 0):
+    """One image: spx (H,W) i32|i64, target (H,W) u8 train ids (255 = ignore), keep (nseg,) u8
+    -> (multi_hot (nseg, num_classes+1) u8, size (nseg,) i32).  See ``mas_multihot_labels_dev``."""
+    _want(spx, "superpixel", (torch.int32, torch.int64), 2)
+    _want(target, "target", torch.uint8, 2)
+    _want(keep, "keep", torch.uint8, 1)
+    h, w = spx.shape
+    if tuple(target.shape) != (h, w) or keep.numel() != nseg:
+        raise RuntimeError("target / keep shapes do not match the superpixel map")
+    multi_hot = torch.empty((nseg, num_classes + 1), dtype=torch.uint8, device=spx.device)
+    size = torch.empty((nseg,), dtype=torch.int32, device=spx.device)
+    need = int(_lib.load().mas_multihot_labels_workspace_bytes(int(nseg), int(num_classes)))
+    ws = torch.empty(need, dtype=torch.uint8, device=spx.device)
+    with torch.cuda.device(spx.device):
+        _lib.call("mas_multihot_labels_dev", spx.data_ptr(), _ids_dtype(spx), target.data_ptr(), keep.data_ptr(), h, w,
+                  int(nseg), int(num_classes), int(trim_kernel_size), multi_hot.data_ptr(), size.data_ptr(), ws.data_ptr(),
+                  need, _stream(spx))
+    return multi_hot, size

@@ -242,6 +242,47 @@ def gen_labeller():
     print("labeller.npz", len(out), "arrays")
 
 
+def gen_labelgen():
+    """dataloader/region_cityscapes_tensor.py:23-84 ``RegionCityscapesTensor.__getitem__`` (offline multi-hot labels),
+    run unmodified with its file I/O stubbed out (PIL open / transform / open_spx / encode_target)."""
+    mod = importlib.import_module("dataloader.region_cityscapes_tensor")
+
+    class _FakeImage:
+        def convert(self, *_):
+            return self
+
+    mod.Image = types.SimpleNamespace(open=lambda *_a, **_k: _FakeImage())
+    out = {}
+    h, w, nseg, c = 40, 64, 24, 7
+    for case, (trim, k, seed, kind) in {"notrim": (False, 3, 51, "jitter"), "trim3": (True, 3, 52, "jitter"),
+                                        "trim5": (True, 5, 53, "jitter"), "trim2_random": (True, 2, 54, "random")}.items():
+        spx = synth.superpixel_map(1, h, w, nseg, kind, seed=seed, drop_ids=1)[0]
+        g = torch.Generator().manual_seed(seed)
+        coarse = torch.randint(0, c, (1, 1, h // 8, w // 8), generator=g).float()
+        target = torch.nn.functional.interpolate(coarse, size=(h, w), mode="nearest")[0, 0].long()
+        target[torch.rand((h, w), generator=g) < 0.08] = 255
+        target[spx == 3] = 255                                    # an all-ignore superpixel
+        ids = sorted(set(torch.unique(spx).tolist()) - {5})       # one id not preserved -> zero row, size -1
+        ds = mod.RegionCityscapesTensor.__new__(mod.RegionCityscapesTensor)
+        ds.args = types.SimpleNamespace(nseg=nseg, num_classes=c, trim_multihot_boundary=trim, trim_kernel_size=k)
+        ds.kernel = np.ones((k, k), np.uint8)
+        ds.im_idx = [["img", "lbl", "spx"]]
+        ds.suppix = {"spx": ids}
+        ds.transform = lambda image, lbls: (image, lbls)
+        ds.open_spx = lambda _f, _spx=spx: _spx.clone()
+        ds.encode_target = lambda t: t
+        mod.Image.open = lambda f, _t=target: _FakeImage() if f == "img" else _t.clone()
+        cls, size = ds.__getitem__(0)["superpixel_info"]
+        out[f"{case}/spx"] = spx.numpy().astype(np.int32)
+        out[f"{case}/target"] = target.numpy().astype(np.uint8)
+        out[f"{case}/ids"] = np.asarray(ids, dtype=np.int32)
+        out[f"{case}/meta"] = np.asarray([nseg, c, k if trim else 0], dtype=np.int32)
+        out[f"{case}/multi_hot"] = cls.numpy()
+        out[f"{case}/size"] = size.numpy().astype(np.int32)
+    np.savez_compressed(os.path.join(GOLDEN, "labelgen.npz"), **out)
+    print("labelgen.npz", len(out), "arrays")
+
+
 def main():
     ref_shims.install()
     os.makedirs(GOLDEN, exist_ok=True)
@@ -250,6 +291,7 @@ def main():
     gen_selection()
     gen_losses()
     gen_labeller()
+    gen_labelgen()
 
 
 if __name__ == "__main__":
