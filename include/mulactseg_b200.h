@@ -205,6 +205,10 @@ int mas_multihot_info_dev(const uint8_t* targets, int64_t n_regions, int target_
  */
 #define MAS_LOSS_CHOICE 1
 #define MAS_LOSS_GROUP 2
+/* softmax in the reference's own operation order (x / T, max-subtract, expf, divide by the sum) instead of the fast
+ * ex2 / reciprocal form (<= 4 ulp apart): for callers that need the arg-max PIXEL of the max-pool to agree with torch
+ * on near-ties (the stage-2 prototype labeller).  Forward only. */
+#define MAS_LOSS_EXACT_SOFTMAX 4
 int mas_multihot_loss_fwd_dev(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask, const uint32_t* info,
                               int n_img, int channels, int height, int width, int nseg, float temperature, int flags,
                               double* acc, uint64_t* group_max, void* stream);

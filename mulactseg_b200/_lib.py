@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmulactseg_b200.so")
 MAS_F32, MAS_BF16 = 0, 1
 MAS_I32, MAS_I64 = 0, 1
 MAS_GROUP_ALL, MAS_GROUP_ONLYMULTI = 0, 1
-MAS_LOSS_CHOICE, MAS_LOSS_GROUP = 1, 2
+MAS_LOSS_CHOICE, MAS_LOSS_GROUP, MAS_LOSS_EXACT_SOFTMAX = 1, 2, 4
 MAS_MAX_LOSS_CLASSES = 31
 MAS_THRESHOLD_MEDIAN, MAS_THRESHOLD_MIN = 0, 1
 

@@ -511,7 +511,7 @@ extern "C" int mas_proto_labeller_dev(const float* feats, int feat_channels, con
                                    w.info, stream);
     if (rc != 0) return rc;
     rc = mas_multihot_loss_fwd_dev(logits, ids, ids_dtype, mask, w.info, 1, channels, height, width, nseg, 1.0f,
-                                   MAS_LOSS_CHOICE | MAS_LOSS_GROUP, w.acc, reinterpret_cast<uint64_t*>(w.gmax), stream);
+                                   MAS_LOSS_CHOICE | MAS_LOSS_GROUP | MAS_LOSS_EXACT_SOFTMAX, w.acc, reinterpret_cast<uint64_t*>(w.gmax), stream);
     if (rc != 0) return rc;
     labeller_status_kernel<<<1, 1, 0, st>>>(w.acc, only_multihot, status);
     mas::count_launches(1);

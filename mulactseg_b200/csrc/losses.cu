@@ -18,7 +18,6 @@
 // keeps that superpixel's running maxima in a private shared-memory column; global atomicMax only when
 // the superpixel changes.  Backward recomputes the softmax and writes the dense gradient once.
 #include "common.cuh"
-#include "walk.cuh"
 
 #include <algorithm>
 
@@ -36,8 +35,7 @@ struct LossParams {
     int n_img, C, H, W, S;
     float temp;      // T
     float inv_temp;  // 1 / T
-    int strips;
-    long long total_rows;
+    float scale;     // log2(e) / T
     int do_choice, do_group;
     double* acc;                  // fwd: [0..5] one-hot / multi-hot / empty {sum, count}
     unsigned long long* gmax;     // (n_img * S * C) packed maxima
@@ -61,202 +59,152 @@ __global__ void multihot_info_kernel(const uint8_t* __restrict__ targets, long l
     info[r] = bits | (in_group ? kGroupBit : 0u);
 }
 
-// ------------------------------------------------------------------------------------------ loads
-template <int VEC>
-__device__ __forceinline__ uint32_t load_mask(const uint8_t* p);   // byte j of the result = mask of pixel j
-template <>
-__device__ __forceinline__ uint32_t load_mask<4>(const uint8_t* p) { return __ldcs(reinterpret_cast<const uint32_t*>(p)); }
-template <>
-__device__ __forceinline__ uint32_t load_mask<1>(const uint8_t* p) { return __ldcs(p); }
+// ------------------------------------------------------------------------------------------ per-pixel pieces
+// Work decomposition of both kernels: one WARP per tile of 32 pixels x kTileRows rows (lane = column), one
+// pixel per thread per row, many more tiles than resident warps: the hardware scheduler balances the very uneven
+// cost of rows (an unselected row is one 32-byte mask load; a selected pixel is a C'-wide softmax).  A thread walks
+// DOWN its column, so it stays inside one superpixel for many rows (private running maxima, see the header).
+constexpr int kTileRows = 16;
 
 __device__ __forceinline__ int clamp_id(long long v) { return (v < 0 || v > 0x7fffffffLL) ? -1 : (int)v; }
 
-template <typename IdT, int VEC>
-struct IdLoad;
-template <>
-struct IdLoad<int32_t, 4> {
-    static __device__ __forceinline__ void load(const int32_t* p, int (&o)[4]) {
-        const int4 v = __ldcs(reinterpret_cast<const int4*>(p));
-        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-    }
-};
-template <>
-struct IdLoad<int32_t, 1> {
-    static __device__ __forceinline__ void load(const int32_t* p, int (&o)[1]) { o[0] = __ldcs(p); }
-};
-template <>
-struct IdLoad<long long, 4> {
-    static __device__ __forceinline__ void load(const long long* p, int (&o)[4]) {
-        const longlong2 a = __ldcs(reinterpret_cast<const longlong2*>(p));
-        const longlong2 b = __ldcs(reinterpret_cast<const longlong2*>(p) + 1);
-        o[0] = clamp_id(a.x); o[1] = clamp_id(a.y); o[2] = clamp_id(b.x); o[3] = clamp_id(b.y);
-    }
-};
-template <>
-struct IdLoad<long long, 1> {
-    static __device__ __forceinline__ void load(const long long* p, int (&o)[1]) { o[0] = clamp_id(__ldcs(p)); }
-};
-
-template <int VEC>
-__device__ __forceinline__ void load_logits(const float* p, float (&o)[VEC]);
-template <>
-__device__ __forceinline__ void load_logits<4>(const float* p, float (&o)[4]) {
-    const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
-    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+template <typename IdT>
+__device__ __forceinline__ int load_id(const void* ids, size_t i) {
+    return clamp_id((long long)__ldcs(reinterpret_cast<const IdT*>(ids) + i));
 }
-template <>
-__device__ __forceinline__ void load_logits<1>(const float* p, float (&o)[1]) { o[0] = __ldcs(p); }
 
-template <int VEC>
-__device__ __forceinline__ void store_grad(float* p, const float (&o)[VEC]);
-template <>
-__device__ __forceinline__ void store_grad<4>(float* p, const float (&o)[4]) {
-    __stcs(reinterpret_cast<float4*>(p), make_float4(o[0], o[1], o[2], o[3]));
-}
-template <>
-__device__ __forceinline__ void store_grad<1>(float* p, const float (&o)[1]) { __stcs(p, o[0]); }
-
-// softmax(x / T) of pixel j in place: v[c][j] <- P_c.  Same operations as the reference's F.softmax(inputs / T):
-// divide by T, subtract the maximum, accurate expf, divide by the sum -- the arg-max pixel of a max-pool and the
-// -log of small probabilities are sensitive to the last bits, and only selected pixels pay for it.
-template <int CMAX, int VEC>
-__device__ __forceinline__ void softmax_inplace(float (&v)[CMAX][VEC], int j, float temp) {
+// softmax(x / T) in place: v[c] <- P_c.
+//  ACCURATE: the reference's own operation order (divide by T, subtract the maximum, expf, divide by the sum) -- used
+//            where the arg-max PIXEL of a max-pool must agree with torch to the last bit (stage-2 prototypes);
+//  fast    : ex2.approx((x - max) * log2e / T) and one reciprocal (<= 4 ulp): the losses (1e-5 tolerance).
+template <int CMAX, bool ACCURATE>
+__device__ __forceinline__ void softmax_inplace(float (&v)[CMAX], float temp, float scale) {
+    if (ACCURATE) {
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) v[c][j] = __fdiv_rn(v[c][j], temp);   // padded planes hold -inf
-    float mx = v[0][j];
-#pragma unroll
-    for (int c = 1; c < CMAX; ++c) mx = fmaxf(mx, v[c][j]);
-    float sum = 0.f;
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
-        v[c][j] = expf(v[c][j] - mx);
-        sum += v[c][j];
+        for (int c = 0; c < CMAX; ++c) v[c] = __fdiv_rn(v[c], temp);   // padded planes hold -inf
     }
+    float mx = v[0];
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) v[c][j] = __fdiv_rn(v[c][j], sum);
+    for (int c = 1; c < CMAX; ++c) mx = fmaxf(mx, v[c]);
+    float sa = 0.f, sb = 0.f;
+    if (ACCURATE) {
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) { v[c] = expf(v[c] - mx); sa += v[c]; }
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) v[c] = __fdiv_rn(v[c], sa);
+    } else {
+        const float shift = -mx * scale;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            v[c] = mas::ex2_approx(fmaf(v[c], scale, shift));
+            if (c & 1) sb += v[c]; else sa += v[c];
+        }
+        const float inv = 1.f / (sa + sb);
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) v[c] *= inv;
+    }
+}
+
+struct Tile {
+    int img, x, y0, y1;
+    bool in_range;
+};
+
+__device__ __forceinline__ Tile my_tile(const LossParams& p) {
+    Tile t;
+    const long long tile = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int tiles_x = (p.W + 31) / 32, tiles_y = (p.H + kTileRows - 1) / kTileRows;
+    const long long per_img = (long long)tiles_x * tiles_y;
+    t.in_range = tile < per_img * p.n_img;
+    t.img = (int)(tile / per_img);
+    const int rem = (int)(tile - (long long)t.img * per_img);
+    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    t.x = tx * 32 + (threadIdx.x & 31);
+    t.y0 = ty * kTileRows;
+    t.y1 = min(p.H, t.y0 + kTileRows);
+    return t;
 }
 
 // ------------------------------------------------------------------------------------------ forward
-template <int CMAX, bool EXACT, int VEC, typename IdT>
+template <int CMAX, bool EXACT, typename IdT, bool ACCURATE>
 __global__ void __launch_bounds__(kThreads) multihot_loss_fwd_kernel(const LossParams p) {
     extern __shared__ unsigned long long gcol[];   // [C][kThreads] running maxima of the thread's current superpixel
     const int tid = threadIdx.x, lane = tid & 31;
     const int C = EXACT ? CMAX : p.C;
     unsigned long long* col = gcol + tid;
-    for (int c = 0; c < C; ++c) col[c * kThreads] = 0ull;
-
-    long long r0, r1;
-    mas::warp_range(p.total_rows, (long long)blockIdx.x * (kThreads / 32) + (tid >> 5), (long long)gridDim.x * (kThreads / 32), r0, r1);
-
+    const Tile t = my_tile(p);
     float sum_one = 0.f, sum_multi = 0.f, sum_empty = 0.f;
     int n_one = 0, n_multi = 0, n_empty = 0;
-    int cur = -1;
-    long long cur_base = 0;   // table offset of superpixel `cur`
 
-    auto flush = [&]() {
-        if (cur < 0) return;
-        for (int c = 0; c < C; ++c) {
-            const unsigned long long e = col[c * kThreads];
-            if (e != 0ull) {
-                atomicMax(p.gmax + cur_base + c, e);
-                col[c * kThreads] = 0ull;
-            }
+    if (t.in_range) {     // warp-uniform
+        if (p.do_group) {
+            for (int c = 0; c < C; ++c) col[c * kThreads] = 0ull;
         }
-        cur = -1;
-    };
-
-    if (r0 < r1) {
-        mas::Cursor at;
-        at.seek(r0, p.strips, p.H);
+        int cur = -1;
+        long long cur_base = 0;   // table offset of superpixel `cur`
         const size_t P = (size_t)p.H * p.W;
-        for (long long r = r0; r < r1; ++r) {
-            const int x0 = (at.strip * 32 + lane) * VEC;
-            if (x0 < p.W) {
-                const size_t off = (size_t)at.y * p.W + x0;
-                const size_t pix0 = (size_t)at.img * P + off;
-                const uint32_t m = load_mask<VEC>(p.mask + pix0);
-                if (m != 0u) {
-                    int id[VEC];
-                    IdLoad<IdT, VEC>::load(reinterpret_cast<const IdT*>(p.ids) + pix0, id);
-                    uint32_t inf[VEC];
-                    bool any_valid = false, any_group = false, touches = false;
-                    int first_group = -1;
+        const bool active = t.x < p.W;
+        for (int y = t.y0; y < t.y1; ++y) {
+            const size_t off = (size_t)y * p.W + t.x;
+            const size_t pix = (size_t)t.img * P + off;
+            const bool m = active && __ldcs(p.mask + pix) != 0;
+            if (!__any_sync(0xffffffffu, m)) continue;          // whole row unselected: nothing else is read
+            if (!m) continue;
+            const int id = load_id<IdT>(p.ids, pix);
+            if ((unsigned)id >= (unsigned)p.S) continue;
+            const uint32_t inf = __ldg(p.info + (size_t)t.img * p.S + id);
+            const uint32_t bits = inf & ~kGroupBit;
+            const bool group = p.do_group && (inf & kGroupBit) && bits != 0u;
+            if (!p.do_choice && !group) continue;
+            float v[CMAX];
+            const float* base = p.logits + (size_t)t.img * C * P + off;
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        const bool valid = ((m >> (8 * j)) & 0xffu) != 0u && (unsigned)id[j] < (unsigned)p.S;
-                        inf[j] = 0u;
-                        if (valid) {
-                            inf[j] = __ldg(p.info + (size_t)at.img * p.S + id[j]);
-                            any_valid = true;
-                            if (p.do_group && (inf[j] & kGroupBit)) {
-                                any_group = true;
-                                touches |= (id[j] == cur);
-                                if (first_group < 0) first_group = id[j];
-                            }
-                        } else {
-                            id[j] = -1;
+            for (int c = 0; c < CMAX; ++c) v[c] = (EXACT || c < C) ? __ldcs(base + (size_t)c * P) : -INFINITY;
+            softmax_inplace<CMAX, ACCURATE>(v, p.temp, p.scale);
+            if (p.do_choice) {
+                float pos = 0.f;
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) pos += ((bits >> c) & 1u) ? v[c] : 0.f;
+                const float l = -logf(pos + kEps);
+                const int n = __popc(bits);
+                if (n == 1) { sum_one += l; ++n_one; }
+                else if (n > 1) { sum_multi += l; ++n_multi; }
+                else { sum_empty += l; ++n_empty; }
+            }
+            if (group) {
+                if (id != cur) {
+                    if (cur >= 0) {
+                        for (int c = 0; c < C; ++c) {
+                            const unsigned long long e = col[c * kThreads];
+                            if (e != 0ull) { atomicMax(p.gmax + cur_base + c, e); col[c * kThreads] = 0ull; }
                         }
                     }
-                    if (any_valid) {
-                        float v[CMAX][VEC];
-                        const float* base = p.logits + (size_t)at.img * C * P + off;
+                    cur = id;
+                    cur_base = ((long long)t.img * p.S + id) * C;
+                }
+                const unsigned long long low = (unsigned long long)(~(uint32_t)off);
 #pragma unroll
-                        for (int c = 0; c < CMAX; ++c) {
-                            if (EXACT || c < C) {
-                                load_logits<VEC>(base + (size_t)c * P, v[c]);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < VEC; ++j) v[c][j] = -INFINITY;
-                            }
-                        }
-                        if (any_group && !touches) {
-                            flush();
-                            cur = first_group;
-                            cur_base = ((long long)at.img * p.S + cur) * C;
-                        }
-#pragma unroll
-                        for (int j = 0; j < VEC; ++j) {
-                            if (id[j] < 0) continue;
-                            softmax_inplace<CMAX, VEC>(v, j, p.temp);
-                            const uint32_t bits = inf[j] & ~kGroupBit;
-                            if (p.do_choice) {
-                                float pos = 0.f;
-#pragma unroll
-                                for (int c = 0; c < CMAX; ++c) pos += ((bits >> c) & 1u) ? v[c][j] : 0.f;
-                                const float l = -logf(pos + kEps);
-                                const int n = __popc(bits);
-                                if (n == 1) { sum_one += l; ++n_one; }
-                                else if (n > 1) { sum_multi += l; ++n_multi; }
-                                else { sum_empty += l; ++n_empty; }
-                            }
-                            if (p.do_group && (inf[j] & kGroupBit)) {
-                                const unsigned long long low = (unsigned long long)(~(uint32_t)(off + j));
-                                const bool own = id[j] == cur;
-                                const long long tbase = ((long long)at.img * p.S + id[j]) * C;
-#pragma unroll
-                                for (int c = 0; c < CMAX; ++c) {
-                                    if ((bits >> c) & 1u) {
-                                        const unsigned long long key = ((unsigned long long)__float_as_uint(v[c][j]) << 32) | low;
-                                        if (own) {
-                                            const unsigned long long old = col[c * kThreads];
-                                            if (key > old) col[c * kThreads] = key;
-                                        } else {
-                                            atomicMax(p.gmax + tbase + c, key);
-                                        }
-                                    }
-                                }
-                            }
-                        }
+                for (int c = 0; c < CMAX; ++c) {
+                    if ((bits >> c) & 1u) {
+                        const unsigned long long key = ((unsigned long long)__float_as_uint(v[c]) << 32) | low;
+                        if (key > col[c * kThreads]) col[c * kThreads] = key;
                     }
                 }
             }
-            const int step = at.advance(p.strips, p.H);
-            if (step == 2) flush();
         }
-        flush();
+        if (cur >= 0) {
+            for (int c = 0; c < C; ++c) {
+                const unsigned long long e = col[c * kThreads];
+                if (e != 0ull) atomicMax(p.gmax + cur_base + c, e);
+            }
+        }
     }
 
     if (p.do_choice) {
+        __shared__ float s_sum[3];
+        __shared__ int s_cnt[3];
+        if (tid < 3) { s_sum[tid] = 0.f; s_cnt[tid] = 0; }
+        __syncthreads();
         float s[3] = {sum_one, sum_multi, sum_empty};
         int n[3] = {n_one, n_multi, n_empty};
 #pragma unroll
@@ -266,10 +214,12 @@ __global__ void __launch_bounds__(kThreads) multihot_loss_fwd_kernel(const LossP
                 s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
                 n[k] += __shfl_xor_sync(0xffffffffu, n[k], o);
             }
-            if (lane == 0 && n[k] != 0) {
-                atomicAdd(p.acc + 2 * k, (double)s[k]);
-                atomicAdd(p.acc + 2 * k + 1, (double)n[k]);
-            }
+            if (lane == 0 && n[k] != 0) { atomicAdd(&s_sum[k], s[k]); atomicAdd(&s_cnt[k], n[k]); }
+        }
+        __syncthreads();
+        if (tid < 3 && s_cnt[tid] != 0) {
+            atomicAdd(p.acc + 2 * tid, (double)s_sum[tid]);
+            atomicAdd(p.acc + 2 * tid + 1, (double)s_cnt[tid]);
         }
     }
 }
@@ -300,157 +250,103 @@ __global__ void group_loss_reduce_kernel(const unsigned long long* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------ backward
-template <int CMAX, bool EXACT, int VEC, typename IdT>
+template <int CMAX, bool EXACT, typename IdT>
 __global__ void __launch_bounds__(kThreads) multihot_loss_bwd_kernel(const LossParams p) {
-    const int tid = threadIdx.x, lane = tid & 31;
     const int C = EXACT ? CMAX : p.C;
-    long long r0, r1;
-    mas::warp_range(p.total_rows, (long long)blockIdx.x * (kThreads / 32) + (tid >> 5), (long long)gridDim.x * (kThreads / 32), r0, r1);
-    if (r0 >= r1) return;
+    const Tile t = my_tile(p);
+    if (!t.in_range || t.x >= p.W) return;
     const float w_one = p.coef[0] * p.inv_temp, w_multi = p.coef[1] * p.inv_temp, w_group = p.coef[3] * p.inv_temp;
-    mas::Cursor at;
-    at.seek(r0, p.strips, p.H);
     const size_t P = (size_t)p.H * p.W;
-    for (long long r = r0; r < r1; ++r, at.advance(p.strips, p.H)) {
-        const int x0 = (at.strip * 32 + lane) * VEC;
-        if (x0 >= p.W) continue;
-        const size_t off = (size_t)at.y * p.W + x0;
-        const size_t pix0 = (size_t)at.img * P + off;
-        float* gbase = p.grad + (size_t)at.img * C * P + off;
-        const uint32_t m = load_mask<VEC>(p.mask + pix0);
-        int id[VEC];
-        uint32_t inf[VEC];
-        bool any_valid = false;
-        if (m != 0u) {
-            IdLoad<IdT, VEC>::load(reinterpret_cast<const IdT*>(p.ids) + pix0, id);
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const bool valid = ((m >> (8 * j)) & 0xffu) != 0u && (unsigned)id[j] < (unsigned)p.S;
-                inf[j] = valid ? __ldg(p.info + (size_t)at.img * p.S + id[j]) : 0u;
-                if (!valid) id[j] = -1;
-                any_valid |= valid;
-            }
+    for (int y = t.y0; y < t.y1; ++y) {
+        const size_t off = (size_t)y * p.W + t.x;
+        const size_t pix = (size_t)t.img * P + off;
+        float* gbase = p.grad + (size_t)t.img * C * P + off;
+        int id = -1;
+        uint32_t inf = 0u;
+        if (__ldcs(p.mask + pix) != 0) {
+            id = load_id<IdT>(p.ids, pix);
+            if ((unsigned)id < (unsigned)p.S) inf = __ldg(p.info + (size_t)t.img * p.S + id); else id = -1;
         }
-        if (!any_valid) {
-            float z[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) z[j] = 0.f;
-            for (int c = 0; c < C; ++c) store_grad<VEC>(gbase + (size_t)c * P, z);
+        const uint32_t bits = inf & ~kGroupBit;
+        const bool group = p.do_group && (inf & kGroupBit) && bits != 0u;
+        if (id < 0 || (!group && !(p.do_choice && bits != 0u))) {      // no gradient reaches this pixel
+            for (int c = 0; c < C; ++c) __stcs(gbase + (size_t)c * P, 0.f);
             continue;
         }
-        float v[CMAX][VEC];
-        const float* base = p.logits + (size_t)at.img * C * P + off;
+        float v[CMAX];
+        const float* base = p.logits + (size_t)t.img * C * P + off;
 #pragma unroll
-        for (int c = 0; c < CMAX; ++c) {
-            if (EXACT || c < C) {
-                load_logits<VEC>(base + (size_t)c * P, v[c]);
-            } else {
+        for (int c = 0; c < CMAX; ++c) v[c] = (EXACT || c < C) ? __ldcs(base + (size_t)c * P) : -INFINITY;
+        softmax_inplace<CMAX, false>(v, p.temp, p.scale);
+        float pos = 0.f;
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) v[c][j] = -INFINITY;
-            }
+        for (int c = 0; c < CMAX; ++c) pos += ((bits >> c) & 1u) ? v[c] : 0.f;
+        float a = 0.f;
+        if (p.do_choice) {
+            const int n = __popc(bits);
+            a = -(n == 1 ? w_one : w_multi) / (pos + kEps);
         }
+        uint32_t abits = 0u;   // classes whose max-pooled probability comes from this pixel
+        float q_sum = 0.f;
+        if (group) {
+            const uint32_t low = ~(uint32_t)off;
+            const unsigned long long* row = p.gmax + ((long long)t.img * p.S + id) * C;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            if (id[j] < 0) {
-#pragma unroll
-                for (int c = 0; c < CMAX; ++c) v[c][j] = 0.f;
-                continue;
-            }
-            softmax_inplace<CMAX, VEC>(v, j, p.temp);
-            const uint32_t bits = inf[j] & ~kGroupBit;
-            float pos = 0.f;
-#pragma unroll
-            for (int c = 0; c < CMAX; ++c) pos += ((bits >> c) & 1u) ? v[c][j] : 0.f;
-            float a = 0.f;
-            if (p.do_choice) {
-                const int n = __popc(bits);
-                const float wb = n == 1 ? w_one : (n > 1 ? w_multi : 0.f);
-                a = -wb / (pos + kEps);
-            }
-            uint32_t abits = 0u;   // classes whose max-pooled probability comes from this pixel
-            float q_sum = 0.f;
-            if (p.do_group && (inf[j] & kGroupBit)) {
-                const uint32_t low = ~(uint32_t)(off + j);
-                const unsigned long long* row = p.gmax + ((long long)at.img * p.S + id[j]) * C;
-#pragma unroll
-                for (int c = 0; c < CMAX; ++c) {
-                    if ((bits >> c) & 1u) {
-                        const unsigned long long e = __ldg(row + c);
-                        if ((uint32_t)e == low && (e >> 32) != 0ull) {
-                            abits |= 1u << c;
-                            q_sum += v[c][j] / (v[c][j] + kEps);
-                        }
+            for (int c = 0; c < CMAX; ++c) {
+                if ((bits >> c) & 1u) {
+                    const unsigned long long e = __ldg(row + c);
+                    if ((uint32_t)e == low && (e >> 32) != 0ull) {
+                        abits |= 1u << c;
+                        q_sum += v[c] / (v[c] + kEps);
                     }
                 }
             }
-#pragma unroll
-            for (int c = 0; c < CMAX; ++c) {
-                const float pc = v[c][j];
-                float g = a * pc * ((((bits >> c) & 1u) ? 1.f : 0.f) - pos);
-                if (abits) g -= w_group * ((((abits >> c) & 1u) ? pc / (pc + kEps) : 0.f) - pc * q_sum);
-                v[c][j] = g;
-            }
         }
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) {
-            if (EXACT || c < C) store_grad<VEC>(gbase + (size_t)c * P, v[c]);
+            const float pc = v[c];
+            float g = a * pc * ((((bits >> c) & 1u) ? 1.f : 0.f) - pos);
+            if (abits) g -= w_group * ((((abits >> c) & 1u) ? pc / (pc + kEps) : 0.f) - pc * q_sum);
+            if (EXACT || c < C) __stcs(gbase + (size_t)c * P, g);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------ launch
-template <typename K>
-int resident_blocks(K kernel, size_t smem) {
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem) != cudaSuccess || n < 1) n = 1;
-    return n;
-}
-
-template <int CMAX, bool EXACT, int VEC, typename IdT>
-cudaError_t launch_one(LossParams p, bool backward, cudaStream_t stream) {
-    p.strips = (p.W + 32 * VEC - 1) / (32 * VEC);
-    p.total_rows = (long long)p.n_img * p.strips * p.H;
-    const long long cap = (p.total_rows + 8 * (kThreads / 32) - 1) / (8 * (kThreads / 32));
+template <int CMAX, bool EXACT, typename IdT>
+cudaError_t launch_one(const LossParams& p, bool backward, bool accurate, cudaStream_t stream) {
+    const long long tiles = (long long)p.n_img * ((p.W + 31) / 32) * ((p.H + kTileRows - 1) / kTileRows);
+    const long long blocks = (tiles + kThreads / 32 - 1) / (kThreads / 32);
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     if (backward) {
-        auto kernel = multihot_loss_bwd_kernel<CMAX, EXACT, VEC, IdT>;
-        static int per_sm = 0;
-        if (per_sm == 0) per_sm = resident_blocks(kernel, 0);
-        const long long blocks = std::max<long long>(1, std::min<long long>((long long)mas::sm_count() * per_sm, cap));
-        kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+        multihot_loss_bwd_kernel<CMAX, EXACT, IdT><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
     } else {
-        auto kernel = multihot_loss_fwd_kernel<CMAX, EXACT, VEC, IdT>;
-        const size_t smem = (size_t)p.C * kThreads * sizeof(unsigned long long);
-        static int per_sm = 0;
-        if (per_sm == 0) per_sm = resident_blocks(kernel, (size_t)CMAX * kThreads * sizeof(unsigned long long));
-        const long long blocks = std::max<long long>(1, std::min<long long>((long long)mas::sm_count() * per_sm, cap));
-        kernel<<<(unsigned)blocks, kThreads, smem, stream>>>(p);
+        const size_t smem = p.do_group ? (size_t)p.C * kThreads * sizeof(unsigned long long) : 0;
+        if (accurate) multihot_loss_fwd_kernel<CMAX, EXACT, IdT, true><<<(unsigned)blocks, kThreads, smem, stream>>>(p);
+        else multihot_loss_fwd_kernel<CMAX, EXACT, IdT, false><<<(unsigned)blocks, kThreads, smem, stream>>>(p);
     }
     mas::count_launches(1);
     return cudaGetLastError();
 }
 
-template <int VEC, typename IdT>
-cudaError_t dispatch_channels(const LossParams& p, bool backward, cudaStream_t stream) {
+template <typename IdT>
+cudaError_t dispatch_channels(const LossParams& p, bool backward, bool accurate, cudaStream_t stream) {
     switch (p.C) {
-        case 19: return launch_one<19, true, VEC, IdT>(p, backward, stream);
-        case 20: return launch_one<20, true, VEC, IdT>(p, backward, stream);
-        case 21: return launch_one<21, true, VEC, IdT>(p, backward, stream);
-        case 22: return launch_one<22, true, VEC, IdT>(p, backward, stream);
+        case 19: return launch_one<19, true, IdT>(p, backward, accurate, stream);
+        case 20: return launch_one<20, true, IdT>(p, backward, accurate, stream);
+        case 21: return launch_one<21, true, IdT>(p, backward, accurate, stream);
+        case 22: return launch_one<22, true, IdT>(p, backward, accurate, stream);
         default: break;
     }
-    if (p.C <= 8) return launch_one<8, false, VEC, IdT>(p, backward, stream);
-    if (p.C <= 16) return launch_one<16, false, VEC, IdT>(p, backward, stream);
-    if (p.C <= 24) return launch_one<24, false, VEC, IdT>(p, backward, stream);
-    return launch_one<31, false, VEC, IdT>(p, backward, stream);
+    if (p.C <= 8) return launch_one<8, false, IdT>(p, backward, accurate, stream);
+    if (p.C <= 16) return launch_one<16, false, IdT>(p, backward, accurate, stream);
+    if (p.C <= 24) return launch_one<24, false, IdT>(p, backward, accurate, stream);
+    return launch_one<31, false, IdT>(p, backward, accurate, stream);
 }
 
-cudaError_t dispatch(const LossParams& p, int ids_dtype, bool backward, cudaStream_t stream) {
-    const size_t id_bytes = ids_dtype == MAS_I64 ? 8 : 4;
-    const bool vec4 = (p.W % 4 == 0) && (((uintptr_t)p.logits) % 16 == 0) && (((uintptr_t)p.ids) % (4 * id_bytes) == 0) &&
-                      (((uintptr_t)p.mask) % 4 == 0) && (!backward || ((uintptr_t)p.grad) % 16 == 0);
-    if (ids_dtype == MAS_I64)
-        return vec4 ? dispatch_channels<4, long long>(p, backward, stream) : dispatch_channels<1, long long>(p, backward, stream);
-    return vec4 ? dispatch_channels<4, int32_t>(p, backward, stream) : dispatch_channels<1, int32_t>(p, backward, stream);
+cudaError_t dispatch(const LossParams& p, int ids_dtype, bool backward, bool accurate, cudaStream_t stream) {
+    if (ids_dtype == MAS_I64) return dispatch_channels<long long>(p, backward, accurate, stream);
+    return dispatch_channels<int32_t>(p, backward, accurate, stream);
 }
 
 int check_common(const char* what, const void* logits, const void* ids, int ids_dtype, const uint8_t* mask, const uint32_t* info,
@@ -461,7 +357,7 @@ int check_common(const char* what, const void* logits, const void* ids, int ids_
                 MAS_MAX_LOSS_CLASSES);
     MAS_REQUIRE(ids_dtype == MAS_I32 || ids_dtype == MAS_I64, MAS_E_BADARG, "%s: bad ids dtype", what);
     MAS_REQUIRE(temperature > 0.f, MAS_E_BADARG, "%s: temperature must be > 0", what);
-    MAS_REQUIRE((flags & ~(MAS_LOSS_CHOICE | MAS_LOSS_GROUP)) == 0 && flags != 0, MAS_E_BADARG, "%s: bad flags", what);
+    MAS_REQUIRE((flags & ~(MAS_LOSS_CHOICE | MAS_LOSS_GROUP | MAS_LOSS_EXACT_SOFTMAX)) == 0 && (flags & (MAS_LOSS_CHOICE | MAS_LOSS_GROUP)) != 0, MAS_E_BADARG, "%s: bad flags", what);
     return 0;
 }
 
@@ -494,11 +390,11 @@ extern "C" int mas_multihot_loss_fwd_dev(const float* logits, const void* ids, i
     LossParams p = {};
     p.logits = logits; p.ids = ids; p.mask = mask; p.info = info;
     p.n_img = n_img; p.C = channels; p.H = height; p.W = width; p.S = nseg;
-    p.temp = temperature; p.inv_temp = 1.f / temperature;
+    p.temp = temperature; p.inv_temp = 1.f / temperature; p.scale = 1.4426950408889634f / temperature;
     p.do_choice = (flags & MAS_LOSS_CHOICE) ? 1 : 0; p.do_group = (flags & MAS_LOSS_GROUP) ? 1 : 0;
     p.acc = acc; p.gmax = reinterpret_cast<unsigned long long*>(group_max);
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = dispatch(p, ids_dtype, false, st);
+    cudaError_t e = dispatch(p, ids_dtype, false, (flags & MAS_LOSS_EXACT_SOFTMAX) != 0, st);
     if (e != cudaSuccess) return mas::cuda_fail(e, "multihot_loss_fwd_kernel launch");
     if (p.do_group) {
         const long long n_regions = (long long)n_img * nseg;
@@ -523,11 +419,11 @@ extern "C" int mas_multihot_loss_bwd_dev(const float* logits, const void* ids, i
     LossParams p = {};
     p.logits = logits; p.ids = ids; p.mask = mask; p.info = info;
     p.n_img = n_img; p.C = channels; p.H = height; p.W = width; p.S = nseg;
-    p.temp = temperature; p.inv_temp = 1.f / temperature;
+    p.temp = temperature; p.inv_temp = 1.f / temperature; p.scale = 1.4426950408889634f / temperature;
     p.do_choice = (flags & MAS_LOSS_CHOICE) ? 1 : 0; p.do_group = (flags & MAS_LOSS_GROUP) ? 1 : 0;
     p.gmax = const_cast<unsigned long long*>(reinterpret_cast<const unsigned long long*>(group_max));
     p.coef = coef; p.grad = grad_logits;
-    cudaError_t e = dispatch(p, ids_dtype, true, (cudaStream_t)stream);
+    cudaError_t e = dispatch(p, ids_dtype, true, false, (cudaStream_t)stream);
     if (e != cudaSuccess) return mas::cuda_fail(e, "multihot_loss_bwd_kernel launch");
     return 0;
 }

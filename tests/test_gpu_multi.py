@@ -1,0 +1,73 @@
+"""Two-GPU path (one process per GPU, NCCL): the pool sharded by image gives the same scores and the same global
+ranking as a single process.  Skipped on boxes with fewer than two GPUs."""
+import os
+import pickle
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as td
+import torch.multiprocessing as mp
+
+from helpers import PoolSet, fake_trainer, selector_args
+from mulactseg_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs():
+    n, c, h, w, nseg = 10, 20, 64, 128, 48
+    logits = synth.logits(n, c, h, w, "cosine", seed=11)
+    spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=12, drop_ids=1)
+    im_idx, suppix = synth.pool_lists(n, nseg, spx, labelled_frac=0.25, seed=13)
+    return logits, spx, im_idx, suppix, nseg, c
+
+
+def _run(method, device, k):
+    import importlib
+    logits, spx, im_idx, suppix, nseg, c = _inputs()
+    mod = importlib.import_module(f"mulactseg_b200.active_selection.{method}")
+    selector = mod.RegionSelector(selector_args(method, nseg, c - 1, True, 0.1, 6.0, 3))
+    pool = PoolSet(logits, spx, im_idx, suppix)
+    ps = selector.score_regions(fake_trainer(device), pool)
+    prefix = selector.ranked_prefix(ps, pool, k)
+    return ps, prefix
+
+
+def _worker(rank, world, port, method, k, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    td.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ps, prefix = _run(method, f"cuda:{rank}", k)
+        with open(os.path.join(out_dir, f"rank{rank}.pkl"), "wb") as f:
+            pickle.dump({"lo": ps.lo, "hi": ps.hi, "scores": ps.scores.cpu().numpy(), "prefix": prefix}, f)
+    finally:
+        td.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("method", ["my_bvsb_predclsbal_pwr_banignore", "my_bvsb_clsbal_v2_banignore", "my_bvsb"])
+def test_two_gpus_match_one(method, tmp_path):
+    k = 60
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, method, k, str(tmp_path)), nprocs=2, join=True)
+    ps, prefix = _run(method, "cuda:0", k)
+    single = ps.scores.cpu().numpy()
+    parts = [pickle.load(open(tmp_path / f"rank{r}.pkl", "rb")) for r in range(2)]
+    assert parts[0]["lo"] == 0 and parts[0]["hi"] == parts[1]["lo"] and parts[1]["hi"] == single.shape[0]
+    both = np.concatenate([parts[0]["scores"], parts[1]["scores"]])
+    # same kernels on the same images; only fp32 atomic order and the exchanged pool-wide scalars can differ
+    np.testing.assert_allclose(both, single, rtol=1e-5, atol=1e-6)
+    assert parts[0]["prefix"] == parts[1]["prefix"]                      # every rank ends with the same ranking
+    got = [(p, i) for _, p, i in parts[0]["prefix"]]
+    want = [(p, i) for _, p, i in prefix]
+    gaps = np.abs(np.diff([s for s, _, _ in prefix]))
+    if np.all(gaps > 1e-5 * max(1.0, abs(prefix[0][0]))):
+        assert got == want
+    else:                                                                # near-ties may swap neighbours
+        assert sorted(got[: k - 5]) == sorted(got[: k - 5]) and len(set(got) & set(want)) >= k - 3

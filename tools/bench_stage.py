@@ -41,7 +41,8 @@ def bench_losses(res, profile):
     spx = synth.pad_border(synth.superpixel_map(n, h, w, nseg, "jitter", seed=2, device=dev), nseg, 16)
     trg = synth.multihot_targets(n, nseg, c, seed=3, device=dev, p_ignore=0.0)
     args = types.SimpleNamespace(nseg=nseg, group_ce_temp=0.1, multi_ce_temp=0.1)
-    for rho in (0.02, 0.2, 1.0):
+    for rho, exact in ((0.02, True), (0.2, True), (1.0, True), (1.0, False)):
+        losses.EXACT_SOFTMAX = exact
         mask = synth.region_mask(spx, nseg, rho, seed=4)
         group, multi = losses.stage1_criterion(args, c - 1)
         xs = [x.clone().requires_grad_(True) for _ in range(3)]   # a fresh `preds` every step, like net(images)
@@ -65,10 +66,10 @@ def bench_losses(res, profile):
         P = h * w
         # algorithmic bytes: mask + int64 ids both directions, logits where selected (fwd + bwd), dense grad
         alg = n * P * ((1 + 8) * 2 + frac * c * 4 * 2 + c * 4)
-        res[f"losses rho={rho}"] = {"fwd_ms": round(ms_f, 4), "fwd_bwd_ms": round(ms_fb, 4), "selected_frac": round(frac, 4),
+        res[f"losses rho={rho} exact_softmax={int(exact)}"] = {"fwd_ms": round(ms_f, 4), "fwd_bwd_ms": round(ms_fb, 4), "selected_frac": round(frac, 4),
                                     "alg_GB": round(alg / 1e9, 3), "GBps": round(alg / ms_fb / 1e6, 1),
                                     "frac_of_measured_hbm": round(alg / ms_fb / 1e6 / peak(), 3)}
-        print(f"losses rho={rho}", res[f"losses rho={rho}"], flush=True)
+        print(f"losses rho={rho} exact_softmax={int(exact)}", res[f"losses rho={rho} exact_softmax={int(exact)}"], flush=True)
 
 
 def bench_labeller(res, profile):
