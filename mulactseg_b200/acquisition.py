@@ -43,20 +43,53 @@ class RegionStats:
     cls_sum (n,S,C) f32 : sum of bvsb over pixels with arg-max class c
     cls_cnt (n,S,C) i32 : pixel count = arg-max histogram (exact)
     prob_sum (n,C)  f64 : sum over pixels of softmax(l/T)   (only when ``need_prob``)
+
+    Consecutive ``add_batch`` launches touch disjoint table rows and only add, so they carry no mutual
+    dependency: with ``lanes`` > 1 they alternate over that many side streams (forked from / joined to the
+    caller's stream with events).  The scorer is a single-wave grid holding a whole SM per CTA, so the CTAs of
+    launch i+1 move onto SMs as the CTAs of launch i retire -- ramp and tail of the ~100 us launches overlap
+    instead of adding a launch gap each.  ``lanes`` = 1 keeps everything on the caller's stream.
     """
 
-    def __init__(self, n_img: int, nseg: int, channels: int, device, need_prob: bool):
+    def __init__(self, n_img: int, nseg: int, channels: int, device, need_prob: bool, lanes: int = 2):
         self.n_img, self.nseg, self.channels = int(n_img), int(nseg), int(channels)
-        self.cls_sum = torch.zeros((n_img, nseg, channels), dtype=torch.float32, device=device)
-        self.cls_cnt = torch.zeros((n_img, nseg, channels), dtype=torch.int32, device=device)
-        self.prob_sum = torch.zeros((n_img, channels), dtype=torch.float64, device=device) if need_prob else None
+        self.lanes = [torch.cuda.Stream(device=device) for _ in range(lanes)] if lanes > 1 else []
+        self._turn, self._dirty = 0, False
+        self._cls_sum = torch.zeros((n_img, nseg, channels), dtype=torch.float32, device=device)
+        self._cls_cnt = torch.zeros((n_img, nseg, channels), dtype=torch.int32, device=device)
+        self._prob_sum = torch.zeros((n_img, channels), dtype=torch.float64, device=device) if need_prob else None
         self.pixels_per_image: Optional[int] = None
 
+    # reading a table orders the caller's stream after the launches still running on the side streams
+    @property
+    def cls_sum(self) -> torch.Tensor:
+        self.join()
+        return self._cls_sum
+
+    @property
+    def cls_cnt(self) -> torch.Tensor:
+        self.join()
+        return self._cls_cnt
+
+    @property
+    def prob_sum(self) -> Optional[torch.Tensor]:
+        self.join()
+        return self._prob_sum
+
+    def join(self):
+        """Make the caller's current stream wait for every outstanding ``add_batch`` launch."""
+        if self._dirty:
+            main = torch.cuda.current_stream(self._cls_sum.device)
+            for lane in self.lanes:
+                main.wait_stream(lane)
+            self._dirty = False
+
     def zero_(self):
-        self.cls_sum.zero_()
-        self.cls_cnt.zero_()
-        if self.prob_sum is not None:
-            self.prob_sum.zero_()
+        self.join()
+        self._cls_sum.zero_()
+        self._cls_cnt.zero_()
+        if self._prob_sum is not None:
+            self._prob_sum.zero_()
 
     def add_batch(self, first_img: int, logits: torch.Tensor, spx: torch.Tensor, temperature: float) -> None:
         """Fold images [first_img, first_img + B) into the tables (asynchronous)."""
@@ -65,12 +98,25 @@ class RegionStats:
             raise RuntimeError(f"batch [{first_img},{first_img + b}) outside the shard of {self.n_img} images")
         if logits.shape[1] != self.channels:
             raise RuntimeError(f"expected {self.channels} channels, got {logits.shape[1]}")
+        if not logits.is_cuda or not spx.is_cuda:
+            raise RuntimeError("add_batch: expected CUDA tensors (there is no CPU path)")
         if spx.dtype != torch.int32:
             spx = spx.to(torch.int32)
         self.pixels_per_image = logits.shape[2] * logits.shape[3]
-        ops.bvsb_segment_stats(logits, spx.contiguous(), self.nseg, temperature,
-                               self.cls_sum[first_img:first_img + b], self.cls_cnt[first_img:first_img + b],
-                               None if self.prob_sum is None else self.prob_sum[first_img:first_img + b])
+        spx = spx.contiguous()
+        tables = (self._cls_sum[first_img:first_img + b], self._cls_cnt[first_img:first_img + b],
+                  None if self._prob_sum is None else self._prob_sum[first_img:first_img + b])
+        if not self.lanes:
+            ops.bvsb_segment_stats(logits, spx, self.nseg, temperature, *tables)
+            return
+        lane = self.lanes[self._turn % len(self.lanes)]
+        self._turn += 1
+        lane.wait_stream(torch.cuda.current_stream(logits.device))   # inputs (and the zeroed tables) are ready
+        with torch.cuda.stream(lane):
+            ops.bvsb_segment_stats(logits, spx, self.nseg, temperature, *tables)
+        logits.record_stream(lane)    # the caching allocator must not recycle them before the lane is done
+        spx.record_stream(lane)
+        self._dirty = True
 
 
 def predicted_class_weights(prob_sum_all: torch.Tensor, pixels_per_image: int, ref_batch: int, coeff: float) -> torch.Tensor:
@@ -95,6 +141,7 @@ def finalize(stats: RegionStats, spec: SelectorSpec, coeff: float = 0.0, ref_bat
     With a process group the pool-wide quantities (class means, min/max, dominant-class histogram) are
     exchanged over it; each rank keeps the scores of its own shard.
     """
+    stats.join()
     weight = None
     if spec.weighting == "predclsbal":
         if stats.prob_sum is None:

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mulactseg_b200 import acquisition as acq, ops, synth  # noqa: E402
 
 
-def time_ms(fn, warmup=3, iters=10):
+def time_ms(fn, warmup=3, iters=10, join=None):
     for i in range(warmup):
         fn(i)
     torch.cuda.synchronize()
@@ -23,6 +23,8 @@ def time_ms(fn, warmup=3, iters=10):
     e0.record()
     for i in range(iters):
         fn(i)
+    if join is not None:
+        join()          # launches alternate over side streams: order the caller's stream after them
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
@@ -51,7 +53,7 @@ def main():
                 stats.add_batch(j, logits[j:j + 4], spx[j:j + 4], 0.1)
             torch.cuda.synchronize()
         return
-    variants = [("tma", {}), ("ldg", {"MAS_SCORER_PATH": "ldg"})]
+    variants = [("tma", {}), ("tma_1lane", {"LANES": "1"}), ("ldg", {"MAS_SCORER_PATH": "ldg"})]
     if not args.quick:
         variants += [("tma_s3_w6", {"MAS_SCORER_STAGES": "3", "MAS_SCORER_WARPS": "6"}),
                      ("tma_s2_w6", {"MAS_SCORER_WARPS": "6"})]
@@ -67,15 +69,15 @@ def main():
                         for name, env in variants:
                             for k in ("MAS_SCORER_PATH", "MAS_SCORER_STAGES", "MAS_SCORER_WARPS"):
                                 os.environ.pop(k, None)
-                            os.environ.update(env)
-                            stats = acq.RegionStats(pool, s, c, dev, need_prob)
+                            os.environ.update({k: v for k, v in env.items() if k != "LANES"})
+                            stats = acq.RegionStats(pool, s, c, dev, need_prob, lanes=int(env.get("LANES", 2)))
                             nb = pool // batch
 
                             def run(i, stats=stats, batch=batch, nb=nb):
                                 j = (i % nb) * batch
                                 stats.add_batch(j, logits[j:j + batch], spx[j:j + batch], 0.1)
 
-                            ms = time_ms(run, iters=6 if kind == "random" else 12)
+                            ms = time_ms(run, iters=6 if kind == "random" else 12, join=stats.join)
                             gb = batch * h * w * (c * logits.element_size() + 4) / 1e9
                             key = f"{name} {str(dtype)[6:]} coherent={coherent} map={kind} B={batch} prob={int(need_prob)}"
                             res[key] = {"ms": round(ms, 4), "GBps": round(gb / ms * 1e3, 1)}
