@@ -222,6 +222,20 @@ int mas_multihot_loss_bwd_dev(const float* logits, const void* ids, int ids_dtyp
                               const uint64_t* group_max, const float* coef, int n_img, int channels, int height, int width,
                               int nseg, float temperature, int flags, float* grad_logits, void* stream);
 
+/* mas_multihot_loss_finish_dev -- the reference's normalisations (counters start at 1; fp32 sum / fp32 count, like
+ * `loss / num_valid`) of the bucket sums in `acc`, in one launch.  losses = 6 DEVICE floats:
+ *   [0] one-hot CE                  acc[0] / (1 + acc[1])                      ..._predignore_lossdecomp.py:69, ..._lossdecomp.py:71
+ *   [1] multi-hot (row-sum > 1)     acc[2] / (1 + acc[3])                      trainer/active_joint_multi_lossdecomp.py:67-72
+ *   [2] multi-hot (not one-hot)     (acc[2] + acc[4]) / (1 + acc[3] + acc[5])  trainer/active_joint_multi_predignore_lossdecomp.py:65-70
+ *   [3] multi-choice CE             (acc[0] + acc[2]) / (1 + acc[1] + acc[3])  utils/loss.py:572-588 (empty rows dropped)
+ *   [4] group / MIL loss            acc[6] / (1 + acc[7])                      utils/loss.py:131-141
+ *   [5] 0
+ * mas_multihot_loss_coef_dev -- its transpose for the backward pass: coef[k] = d(sum_j grad_losses[j] * losses[j]) / d acc[2k]
+ * (4 DEVICE floats, the `coef` argument of mas_multihot_loss_bwd_dev).
+ */
+int mas_multihot_loss_finish_dev(const double* acc, float* losses, void* stream);
+int mas_multihot_loss_coef_dev(const double* acc, const float* grad_losses, float* coef, void* stream);
+
 /* ------------------------------------------------------------------ stage-2 pseudo-labellers
  *
  * mas_candidate_argmax_dev -- trainer/eval_within_multihot.py:93-146 top_pseudo_label_generation:

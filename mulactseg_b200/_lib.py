@@ -43,6 +43,8 @@ SIGNATURES = {
     "mas_multihot_info_dev": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mas_multihot_loss_fwd_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                           c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "mas_multihot_loss_finish_dev": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "mas_multihot_loss_coef_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "mas_candidate_argmax_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                          c_void_p, c_void_p]),
     "mas_proto_labeller_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),

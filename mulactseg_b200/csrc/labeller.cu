@@ -213,41 +213,108 @@ __device__ __forceinline__ bool pixel_selected(const LabelParams& p, int pix, ui
     return (inf & kGroupBit) && p.mask[pix] != 0;
 }
 
-// dot products of pixel `pix` with the kGroup prototypes staged in shared memory (fixed channel order)
-__device__ __forceinline__ void dot_group(const LabelParams& p, const float* sproto, int pix, float (&acc)[kGroup]) {
+// ------------------------------------------------------------------------------------------ similarity engine
+// Both prototype kernels evaluate, for one pixel per thread, the inner products of the pixel's feature column with up
+// to kGroup prototypes staged in shared memory -- ONE pass over the column for all of them, kFeatBatch channel loads in
+// flight per thread (each a coalesced row segment: the pixel list keeps the runs of a superpixel contiguous).
+// Every similarity is the same fp32 FMA chain over channels 0..F-1, whichever kernel computes it.
+constexpr int kFeatBatch = 16;
+constexpr int kSlices = 4;         // CTAs that share the pixels of one superpixel
+
+// sproto layout: [channel][kGroup] so that the kGroup operands of one channel are two 128-bit broadcast reads
+__device__ __forceinline__ void dot_all(const LabelParams& p, const float* __restrict__ sproto, int pix, float (&acc)[kGroup]) {
 #pragma unroll
     for (int g = 0; g < kGroup; ++g) acc[g] = 0.f;
     const float* f = p.feats + pix;
-#pragma unroll 4
-    for (int ch = 0; ch < p.F; ++ch) {
-        const float x = __ldg(f + (size_t)ch * p.P);
+    const size_t P = (size_t)p.P;
+    int ch = 0;
+    for (; ch + kFeatBatch <= p.F; ch += kFeatBatch) {
+        float x[kFeatBatch];
 #pragma unroll
-        for (int g = 0; g < kGroup; ++g) acc[g] = fmaf(x, sproto[g * p.F + ch], acc[g]);
+        for (int i = 0; i < kFeatBatch; ++i) x[i] = __ldg(f + (size_t)(ch + i) * P);
+#pragma unroll
+        for (int i = 0; i < kFeatBatch; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(sproto + (size_t)(ch + i) * kGroup);
+            const float4 b = *reinterpret_cast<const float4*>(sproto + (size_t)(ch + i) * kGroup + 4);
+            acc[0] = fmaf(x[i], a.x, acc[0]); acc[1] = fmaf(x[i], a.y, acc[1]);
+            acc[2] = fmaf(x[i], a.z, acc[2]); acc[3] = fmaf(x[i], a.w, acc[3]);
+            acc[4] = fmaf(x[i], b.x, acc[4]); acc[5] = fmaf(x[i], b.y, acc[5]);
+            acc[6] = fmaf(x[i], b.z, acc[6]); acc[7] = fmaf(x[i], b.w, acc[7]);
+        }
+    }
+    for (; ch < p.F; ++ch) {
+        const float x = __ldg(f + (size_t)ch * P);
+#pragma unroll
+        for (int g = 0; g < kGroup; ++g) acc[g] = fmaf(x, sproto[(size_t)ch * kGroup + g], acc[g]);
     }
 }
+static_assert(kGroup == 8, "dot_all is written for 8 prototypes per pass");
 
-// stage prototypes k0 .. k0+kGroup-1 of superpixel s (classes in ascending order) into shared memory
-__device__ __forceinline__ void stage_protos(const LabelParams& p, float* sproto, int s, uint32_t bits, int k0, int* scls) {
-    // class of the k-th candidate
-    if (threadIdx.x < kGroup) {
-        uint32_t b = bits;
-        int c = -1;
-        for (int k = 0; k <= k0 + (int)threadIdx.x && b; ++k) { c = __ffs(b) - 1; b &= b - 1u; if (k < k0 + (int)threadIdx.x) c = -1; }
-        scls[threadIdx.x] = c;
-    }
-    __syncthreads();
+// One entry of the prototype list a CTA works through: prototype (s, c), in the order the reference visits them.
+struct ProtoEntry {
+    int s, c;
+    int first;      // 1: first prototype of superpixel s (a new neighbour starts here)
+};
+
+// copy the prototypes of ent[0..n) (zeros beyond n) into sproto[channel][slot]; all threads
+__device__ __forceinline__ void stage_entries(const LabelParams& p, float* sproto, const ProtoEntry* ent, int n) {
     for (int i = threadIdx.x; i < kGroup * p.F; i += blockDim.x) {
         const int g = i / p.F, ch = i - g * p.F;
-        const int c = scls[g];
-        sproto[i] = c >= 0 ? p.proto[((size_t)s * p.C + c) * p.F + ch] : 0.f;
+        sproto[(size_t)ch * kGroup + g] = g < n ? p.proto[((size_t)ent[g].s * p.C + ent[g].c) * p.F + ch] : 0.f;
     }
-    __syncthreads();
 }
 
-// one CTA per selected superpixel: nearest prototype of every selected pixel, then the per-prototype threshold
+// ------------------------------------------------------------------------------------------ assign
+// CTA (s, slice): nearest prototype of s for the selected pixels of s in this slice  (:213-230)
 __global__ void __launch_bounds__(kAssignThreads) proto_assign_kernel(LabelParams p) {
-    extern __shared__ float sproto[];          // [kGroup][F]
-    __shared__ int scls[kGroup];
+    extern __shared__ __align__(16) float sproto[];          // [F][kGroup]
+    __shared__ ProtoEntry ent[kGroup];
+    const int s = blockIdx.x;
+    if (!((p.svalid[s >> 5] >> (s & 31)) & 1u)) return;
+    const uint32_t inf = p.info[s];
+    const uint32_t bits = inf & ~kGroupBit;
+    const int beg = p.offset[s], end = p.offset[s + 1];
+    for (int base = beg + blockIdx.y * kAssignThreads; base < end; base += kSlices * kAssignThreads) {
+        const int e = base + threadIdx.x;
+        const int pix = e < end ? p.pixlist[e] : -1;
+        const bool mine = pix >= 0 && pixel_selected(p, pix, inf);
+        float best = -INFINITY;
+        int bestc = 255;
+        uint32_t rest = bits;
+        while (rest) {                                   // uniform over the CTA
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t b = rest;
+                for (int g = 0; g < kGroup; ++g) {
+                    if (b) { ent[g].s = s; ent[g].c = __ffs(b) - 1; ent[g].first = 0; b &= b - 1u; }
+                    else ent[g].c = -1;
+                }
+            }
+            int n = 0;
+            for (; n < kGroup && rest; ++n) rest &= rest - 1u;
+            __syncthreads();
+            stage_entries(p, sproto, ent, n);
+            __syncthreads();
+            if (mine) {
+                float acc[kGroup];
+                dot_all(p, sproto, pix, acc);
+#pragma unroll
+                for (int g = 0; g < kGroup; ++g) {
+                    if (g < n && (acc[g] > best || bestc == 255)) { best = acc[g]; bestc = ent[g].c; }
+                }
+            }
+        }
+        if (mine) {
+            p.own_sim[pix] = best;
+            p.own_cls[pix] = (uint8_t)bestc;
+            p.labels[pix] = (uint8_t)bestc;
+        }
+    }
+}
+
+// one CTA per selected superpixel: per-prototype threshold = lower median (torch.median) or min of the similarities of
+// the pixels assigned to it, 1.0 if none  (:241-255)
+__global__ void __launch_bounds__(kAssignThreads) proto_threshold_kernel(LabelParams p) {
     __shared__ unsigned int hist[256];
     __shared__ unsigned int sel_prefix, sel_rank;
     __shared__ float red[kAssignThreads / 32];
@@ -255,30 +322,7 @@ __global__ void __launch_bounds__(kAssignThreads) proto_assign_kernel(LabelParam
     if (!((p.svalid[s >> 5] >> (s & 31)) & 1u)) return;
     const uint32_t inf = p.info[s];
     const uint32_t bits = inf & ~kGroupBit;
-    const int K = __popc(bits);
     const int beg = p.offset[s], end = p.offset[s + 1];
-
-    for (int k0 = 0; k0 < K; k0 += kGroup) {
-        stage_protos(p, sproto, s, bits, k0, scls);
-        for (int e = beg + threadIdx.x; e < end; e += blockDim.x) {
-            const int pix = p.pixlist[e];
-            if (!pixel_selected(p, pix, inf)) continue;
-            float acc[kGroup];
-            dot_group(p, sproto, pix, acc);
-            float best = k0 == 0 ? -INFINITY : p.own_sim[pix];
-            int bestc = k0 == 0 ? 255 : p.own_cls[pix];
-#pragma unroll
-            for (int g = 0; g < kGroup; ++g) {
-                if (scls[g] >= 0 && (acc[g] > best || bestc == 255)) { best = acc[g]; bestc = scls[g]; }
-            }
-            p.own_sim[pix] = best;
-            p.own_cls[pix] = (uint8_t)bestc;
-            if (k0 + kGroup >= K) p.labels[pix] = (uint8_t)bestc;
-        }
-        __syncthreads();
-    }
-
-    // thresholds: lower median (torch.median) or min of the similarities of the pixels assigned to each prototype
     uint32_t b = bits;
     while (b) {
         const int c = __ffs(b) - 1;
@@ -340,14 +384,20 @@ __global__ void __launch_bounds__(kAssignThreads) proto_assign_kernel(LabelParam
     }
 }
 
-// one CTA per superpixel t: its UNSELECTED pixels take the label offered by the largest adjacent selected superpixel
-// (t itself included) whose test "some threshold < similarity" passes
+// ------------------------------------------------------------------------------------------ propagate
+// CTA (t, slice): the UNSELECTED pixels of superpixel t in this slice take the label offered by the largest adjacent
+// selected superpixel (t itself included) whose test "some threshold < similarity" passes  (:276-305, ascending
+// overwrite order == the largest passing id wins).  The prototypes of the neighbours are walked in that order,
+// kGroup at a time; a pixel stops at its first passing neighbour.
 __global__ void __launch_bounds__(kAssignThreads) proto_propagate_kernel(LabelParams p) {
-    extern __shared__ float sproto[];          // [kGroup][F]
-    __shared__ int scls[kGroup];
+    extern __shared__ __align__(16) float sproto[];          // [F][kGroup]
+    __shared__ ProtoEntry ent[kGroup];
+    __shared__ float ent_thr[kGroup];
+    __shared__ int n_ent, cur_word, cur_s;
+    __shared__ uint32_t cur_bits, cur_cls;
     const int t = blockIdx.x;
     const int beg = p.offset[t], end = p.offset[t + 1];
-    if (beg == end) return;
+    if (beg + (int)blockIdx.y * kAssignThreads >= end) return;
     const uint32_t* row = p.adj + (size_t)t * p.words;
     // any selected neighbour at all?
     bool any = false;
@@ -355,42 +405,72 @@ __global__ void __launch_bounds__(kAssignThreads) proto_propagate_kernel(LabelPa
     if (!any) return;
     const uint32_t inf_t = p.info[t];
 
-    for (int base = beg; base < end; base += blockDim.x) {
+    for (int base = beg + blockIdx.y * kAssignThreads; base < end; base += kSlices * kAssignThreads) {
         const int e = base + threadIdx.x;
         const int pix = e < end ? p.pixlist[e] : -1;
         bool done = pix < 0 || pixel_selected(p, pix, inf_t);   // selected pixels keep their own label
-        for (int w = p.words - 1; w >= 0; --w) {
-            uint32_t m = (row[w] | ((w == (t >> 5)) ? (1u << (t & 31)) : 0u)) & p.svalid[w];
-            while (m) {
-                const int bitpos = 31 - __clz(m);
-                m &= ~(1u << bitpos);
-                const int s = w * 32 + bitpos;
-                if (__syncthreads_and(done)) { m = 0u; w = 0; break; }
-                const uint32_t bits = p.info[s] & ~kGroupBit;
-                const int K = __popc(bits);
-                float best = -INFINITY;
-                int bestc = 255;
-                bool pass = false;
-                for (int k0 = 0; k0 < K; k0 += kGroup) {
-                    stage_protos(p, sproto, s, bits, k0, scls);
-                    if (!done) {
-                        float acc[kGroup];
-                        dot_group(p, sproto, pix, acc);
+        // state of the neighbour being evaluated (its prototypes may span two batches)
+        float best = -INFINITY;
+        int bestc = 255;
+        bool pass = false;
+        __syncthreads();
+        if (threadIdx.x == 0) { cur_word = p.words; cur_bits = 0u; cur_cls = 0u; cur_s = -1; }
+        while (true) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                // next kGroup prototypes: neighbours by descending id, classes ascending
+                int n = 0;
+                int w = cur_word, sidx = cur_s;
+                uint32_t nb = cur_bits, cls = cur_cls;
+                while (n < kGroup) {
+                    if (cls == 0u) {                     // next neighbour
+                        while (nb == 0u && w > 0) {
+                            --w;
+                            nb = (row[w] | ((w == (t >> 5)) ? (1u << (t & 31)) : 0u)) & p.svalid[w];
+                        }
+                        if (nb == 0u) break;
+                        const int bitpos = 31 - __clz(nb);
+                        nb &= ~(1u << bitpos);
+                        sidx = w * 32 + bitpos;
+                        cls = p.info[sidx] & ~kGroupBit;
+                        if (cls == 0u) continue;
+                        ent[n].first = 1;
+                    } else {
+                        ent[n].first = 0;
+                    }
+                    const int c = __ffs(cls) - 1;
+                    cls &= cls - 1u;
+                    ent[n].s = sidx; ent[n].c = c;
+                    ent_thr[n] = p.thr[(size_t)sidx * p.C + c];
+                    ++n;
+                }
+                n_ent = n; cur_word = w; cur_bits = nb; cur_cls = cls; cur_s = sidx;
+            }
+            __syncthreads();
+            const int n = n_ent;
+            if (n == 0) break;
+            stage_entries(p, sproto, ent, n);
+            const bool all_done = __syncthreads_and(done);          // also orders the staging before the reads
+            if (all_done) break;
+            if (!done) {
+                float acc[kGroup];
+                dot_all(p, sproto, pix, acc);
 #pragma unroll
-                        for (int g = 0; g < kGroup; ++g) {
-                            if (scls[g] < 0) continue;
-                            if (acc[g] > best || bestc == 255) { best = acc[g]; bestc = scls[g]; }
-                            pass |= p.thr[(size_t)s * p.C + scls[g]] < acc[g];
+                for (int g = 0; g < kGroup; ++g) {
+                    if (g < n && !done) {
+                        if (ent[g].first) {              // the previous neighbour is complete: did it pass?
+                            if (pass) { p.labels[pix] = (uint8_t)bestc; done = true; }
+                            best = -INFINITY; bestc = 255; pass = false;
+                        }
+                        if (!done) {
+                            if (acc[g] > best || bestc == 255) { best = acc[g]; bestc = ent[g].c; }
+                            pass |= ent_thr[g] < acc[g];
                         }
                     }
-                    __syncthreads();
-                }
-                if (!done && pass) {
-                    p.labels[pix] = (uint8_t)bestc;
-                    done = true;
                 }
             }
         }
+        if (!done && pass) p.labels[pix] = (uint8_t)bestc;
     }
 }
 
@@ -450,9 +530,11 @@ int run_labeller(const LabelParams& p, const Workspace& w, cudaStream_t st) {
     const long long entries = (long long)p.S * p.C;
     proto_gather_kernel<<<(unsigned)((entries * 32 + threads - 1) / threads), threads, 0, st>>>(p);
     const size_t smem = (size_t)kGroup * p.F * sizeof(float);
-    proto_assign_kernel<<<p.S, kAssignThreads, smem, st>>>(p);
-    proto_propagate_kernel<<<p.S, kAssignThreads, smem, st>>>(p);
-    mas::count_launches(7);
+    const dim3 grid_sp((unsigned)p.S, kSlices);
+    proto_assign_kernel<<<grid_sp, kAssignThreads, smem, st>>>(p);
+    proto_threshold_kernel<<<p.S, kAssignThreads, 0, st>>>(p);
+    proto_propagate_kernel<<<grid_sp, kAssignThreads, smem, st>>>(p);
+    mas::count_launches(8);
     MAS_LAUNCH_OK("prototype labeller kernels");
     return 0;
 }

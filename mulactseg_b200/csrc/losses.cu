@@ -60,11 +60,16 @@ __global__ void multihot_info_kernel(const uint8_t* __restrict__ targets, long l
 }
 
 // ------------------------------------------------------------------------------------------ per-pixel pieces
-// Work decomposition of both kernels: one WARP per tile of 32 pixels x kTileRows rows (lane = column), one
-// pixel per thread per row, many more tiles than resident warps: the hardware scheduler balances the very uneven
-// cost of rows (an unselected row is one 32-byte mask load; a selected pixel is a C'-wide softmax).  A thread walks
-// DOWN its column, so it stays inside one superpixel for many rows (private running maxima, see the header).
+// Work decomposition of both kernels: a TILE is 32 pixels x kTileRows rows (lane = column, one pixel per thread per
+// row); the warps of a persistent grid (resident CTAs x SMs) take tiles round-robin, so neighbouring tiles -- which tend
+// to be equally expensive -- land on different warps.  A thread walks DOWN its column, so it stays inside one superpixel
+// for many rows (private running maxima, see the header).  No row waits on a chain of dependent round trips to HBM:
+//   1. the mask bytes of all kTileRows rows are loaded at once (one 32-byte sector per row and warp); a tile without a
+//      selected pixel ends there (forward) or is zero-filled with independent streaming stores (backward);
+//   2. rows are software-pipelined three deep: while row r is computed, the C' logits and the candidate word of row
+//      r + 1 and the id of row r + 2 are in flight (loads of unselected pixels are predicated off).
 constexpr int kTileRows = 16;
+constexpr uint32_t kFullWarp = 0xffffffffu;
 
 __device__ __forceinline__ int clamp_id(long long v) { return (v < 0 || v > 0x7fffffffLL) ? -1 : (int)v; }
 
@@ -73,12 +78,15 @@ __device__ __forceinline__ int load_id(const void* ids, size_t i) {
     return clamp_id((long long)__ldcs(reinterpret_cast<const IdT*>(ids) + i));
 }
 
-// softmax(x / T) in place: v[c] <- P_c.
-//  ACCURATE: the reference's own operation order (divide by T, subtract the maximum, expf, divide by the sum) -- used
-//            where the arg-max PIXEL of a max-pool must agree with torch to the last bit (stage-2 prototypes);
-//  fast    : ex2.approx((x - max) * log2e / T) and one reciprocal (<= 4 ulp): the losses (1e-5 tolerance).
+// softmax(x / T) as numerators + normaliser: v[c] <- e_c = exp(x_c/T - max), returns what turns e_c into P_c.
+//  ACCURATE: the reference's own operation order (divide by T, subtract the maximum, expf, divide by the sum): the
+//            return value is the SUM and P_c = __fdiv_rn(e_c, sum) -- used where the arg-max PIXEL of a max-pool must
+//            agree with torch to the last bit (stage-2 prototypes);
+//  fast    : ex2.approx((x - max) * log2e / T); the return value is 1 / sum and P_c = e_c * that (<= 4 ulp from the
+//            exact form): the losses (1e-5 tolerance).
+// Only the few candidate classes of a pixel ever need P_c, so the C' normalisations are not done here.
 template <int CMAX, bool ACCURATE>
-__device__ __forceinline__ void softmax_inplace(float (&v)[CMAX], float temp, float scale) {
+__device__ __forceinline__ float softmax_numerators(float (&v)[CMAX], float temp, float scale) {
     if (ACCURATE) {
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) v[c] = __fdiv_rn(v[c], temp);   // padded planes hold -inf
@@ -90,136 +98,244 @@ __device__ __forceinline__ void softmax_inplace(float (&v)[CMAX], float temp, fl
     if (ACCURATE) {
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) { v[c] = expf(v[c] - mx); sa += v[c]; }
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c) v[c] = __fdiv_rn(v[c], sa);
-    } else {
-        const float shift = -mx * scale;
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c) {
-            v[c] = mas::ex2_approx(fmaf(v[c], scale, shift));
-            if (c & 1) sb += v[c]; else sa += v[c];
-        }
-        const float inv = 1.f / (sa + sb);
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c) v[c] *= inv;
+        return sa;
     }
+    const float shift = -mx * scale;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        v[c] = mas::ex2_approx(fmaf(v[c], scale, shift));
+        if (c & 1) sb += v[c]; else sa += v[c];
+    }
+    return 1.f / (sa + sb);
 }
 
+template <bool ACCURATE>
+__device__ __forceinline__ float normalised(float e, float norm) { return ACCURATE ? __fdiv_rn(e, norm) : e * norm; }
+
+__device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
 struct Tile {
-    int img, x, y0, y1;
-    bool in_range;
+    int img, x, y0, rows;
 };
 
-__device__ __forceinline__ Tile my_tile(const LossParams& p) {
+__device__ __forceinline__ long long tile_count(const LossParams& p) {
+    return (long long)p.n_img * ((p.W + 31) / 32) * ((p.H + kTileRows - 1) / kTileRows);
+}
+
+__device__ __forceinline__ Tile make_tile(const LossParams& p, long long tile) {
     Tile t;
-    const long long tile = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
     const int tiles_x = (p.W + 31) / 32, tiles_y = (p.H + kTileRows - 1) / kTileRows;
     const long long per_img = (long long)tiles_x * tiles_y;
-    t.in_range = tile < per_img * p.n_img;
     t.img = (int)(tile / per_img);
     const int rem = (int)(tile - (long long)t.img * per_img);
     const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
     t.x = tx * 32 + (threadIdx.x & 31);
     t.y0 = ty * kTileRows;
-    t.y1 = min(p.H, t.y0 + kTileRows);
+    t.rows = min(p.H - t.y0, kTileRows);
     return t;
 }
+
+// Step 1: bit r of the result <-> the pixel of row y0 + r in this thread's column is selected by the mask.
+__device__ __forceinline__ uint32_t tile_mask_bits(const LossParams& p, const Tile& t, size_t pix0) {
+    const bool active = t.x < p.W;
+    uint8_t m[kTileRows];
+#pragma unroll
+    for (int r = 0; r < kTileRows; ++r) m[r] = (active && r < t.rows) ? __ldcs(p.mask + pix0 + (size_t)r * p.W) : (uint8_t)0;
+    uint32_t mbits = 0u;
+#pragma unroll
+    for (int r = 0; r < kTileRows; ++r) mbits |= (m[r] != 0 ? 1u : 0u) << r;
+    return mbits;
+}
+
+// pull the mask bytes of a tile this warp will scan later into L1
+__device__ __forceinline__ void prefetch_tile_mask(const LossParams& p, const Tile& t, size_t pix0) {
+    if (t.x < p.W) {
+#pragma unroll
+        for (int r = 0; r < kTileRows; ++r) {
+            if (r < t.rows) prefetch_l1(p.mask + pix0 + (size_t)r * p.W);
+        }
+    }
+}
+
+constexpr int kPrefetchRows = 4;   // rows ahead of the one being computed whose id + logits are pulled into L1
+
+// Step 2: the three-deep row pipeline of one thread.  After `start`, `next()` hands out rows 0, 1, 2 ... in turn:
+// the logits (raw), the id (-1: not selected / out of range) and the candidate word of the thread's pixel.
+template <int CMAX, bool EXACT, typename IdT>
+struct RowPipe {
+    const LossParams& p;
+    const float* logits;     // plane 0 of the thread's pixel in row 0 of the tile
+    const uint32_t* info;    // candidate words of the image
+    size_t pix, P;
+    uint32_t mbits;
+    int C, r;
+    float vn[CMAX];          // row r (in flight)
+    uint32_t infn;           // row r
+    int idn, idnn;           // rows r, r + 1
+
+    __device__ __forceinline__ RowPipe(const LossParams& params) : p(params) {}
+
+    __device__ __forceinline__ int fetch_id(int row) const {
+        if (!((mbits >> row) & 1u)) return -1;
+        const int id = load_id<IdT>(p.ids, pix + (size_t)row * p.W);
+        return ((unsigned)id < (unsigned)p.S) ? id : -1;
+    }
+    __device__ __forceinline__ void fetch_row(int row, int id) {
+        const bool on = id >= 0;
+        infn = on ? __ldg(info + id) : 0u;
+        const float* ptr = logits + (size_t)row * p.W;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            vn[c] = (EXACT || c < C) ? (on ? __ldcs(ptr) : 0.f) : -INFINITY;
+            ptr += P;       // one 64-bit add per plane
+        }
+    }
+    // L1 prefetch of a row further down (no registers held): the register loads above then hit L1
+    __device__ __forceinline__ void prefetch_row(int row) const {
+        if (row < kTileRows && ((mbits >> row) & 1u)) {
+            prefetch_l1(reinterpret_cast<const IdT*>(p.ids) + pix + (size_t)row * p.W);
+            const float* ptr = logits + (size_t)row * p.W;
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) {
+                if (EXACT || c < C) prefetch_l1(ptr);
+                ptr += P;
+            }
+        }
+    }
+    __device__ __forceinline__ void start(const Tile& t, int channels, size_t plane, size_t off0, uint32_t mask_bits) {
+        C = channels; P = plane; mbits = mask_bits;
+        pix = (size_t)t.img * P + off0;
+        logits = p.logits + (size_t)t.img * C * P + off0;
+        info = p.info + (size_t)t.img * p.S;
+        r = 0;
+        idn = fetch_id(0);
+        idnn = fetch_id(1);
+        fetch_row(0, idn);
+#pragma unroll 1
+        for (int k = 1; k < kPrefetchRows; ++k) prefetch_row(k);
+    }
+    __device__ __forceinline__ void next(float (&v)[CMAX], int& id, uint32_t& inf) {
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) v[c] = vn[c];
+        id = idn; inf = infn;
+        ++r;
+        idn = idnn;
+        idnn = (r + 1 < kTileRows) ? fetch_id(r + 1) : -1;
+        if (r < kTileRows) fetch_row(r, idn);
+        prefetch_row(r + kPrefetchRows - 1);
+    }
+};
 
 // ------------------------------------------------------------------------------------------ forward
 template <int CMAX, bool EXACT, typename IdT, bool ACCURATE>
 __global__ void __launch_bounds__(kThreads) multihot_loss_fwd_kernel(const LossParams p) {
-    extern __shared__ unsigned long long gcol[];   // [C][kThreads] running maxima of the thread's current superpixel
+    // [C][kThreads] u64: running maxima of the thread's current superpixel;  [C][kThreads] f32: softmax numerators of
+    // the pixel being processed (registers cannot be indexed by the candidate class; private columns, no conflicts)
+    extern __shared__ unsigned long long gcol[];
     const int tid = threadIdx.x, lane = tid & 31;
     const int C = EXACT ? CMAX : p.C;
     unsigned long long* col = gcol + tid;
-    const Tile t = my_tile(p);
+    float* pst = reinterpret_cast<float*>(gcol + (size_t)C * kThreads) + tid;
+    const bool do_choice = p.do_choice != 0, do_group = p.do_group != 0;
+    const size_t P = (size_t)p.H * p.W;
     float sum_one = 0.f, sum_multi = 0.f, sum_empty = 0.f;
     int n_one = 0, n_multi = 0, n_empty = 0;
+    if (do_group) {
+        for (int c = 0; c < C; ++c) col[c * kThreads] = 0ull;
+    }
 
-    if (t.in_range) {     // warp-uniform
-        if (p.do_group) {
-            for (int c = 0; c < C; ++c) col[c * kThreads] = 0ull;
+    const long long n_tiles = tile_count(p);
+    const long long warp_stride = (long long)gridDim.x * (kThreads / 32);
+    for (long long tile = (long long)blockIdx.x * (kThreads / 32) + (tid >> 5); tile < n_tiles; tile += warp_stride) {
+        const Tile t = make_tile(p, tile);
+        const size_t off0 = (size_t)t.y0 * p.W + t.x;
+        const uint32_t mbits = tile_mask_bits(p, t, (size_t)t.img * P + off0);
+        if (tile + warp_stride < n_tiles) {
+            const Tile tn = make_tile(p, tile + warp_stride);
+            prefetch_tile_mask(p, tn, (size_t)tn.img * P + (size_t)tn.y0 * p.W + tn.x);
         }
+        const uint32_t any_rows = __reduce_or_sync(kFullWarp, mbits);
+        if (any_rows == 0u) continue;                                                         // warp-uniform
+        RowPipe<CMAX, EXACT, IdT> pipe(p);
+        pipe.start(t, C, P, off0, mbits);
         int cur = -1;
         long long cur_base = 0;   // table offset of superpixel `cur`
-        const size_t P = (size_t)p.H * p.W;
-        const bool active = t.x < p.W;
-        for (int y = t.y0; y < t.y1; ++y) {
-            const size_t off = (size_t)y * p.W + t.x;
-            const size_t pix = (size_t)t.img * P + off;
-            const bool m = active && __ldcs(p.mask + pix) != 0;
-            if (!__any_sync(0xffffffffu, m)) continue;          // whole row unselected: nothing else is read
-            if (!m) continue;
-            const int id = load_id<IdT>(p.ids, pix);
-            if ((unsigned)id >= (unsigned)p.S) continue;
-            const uint32_t inf = __ldg(p.info + (size_t)t.img * p.S + id);
-            const uint32_t bits = inf & ~kGroupBit;
-            const bool group = p.do_group && (inf & kGroupBit) && bits != 0u;
-            if (!p.do_choice && !group) continue;
+#pragma unroll 1
+        for (int r = 0; r < kTileRows; ++r) {
             float v[CMAX];
-            const float* base = p.logits + (size_t)t.img * C * P + off;
+            int id;
+            uint32_t inf;
+            pipe.next(v, id, inf);
+            if (!((any_rows >> r) & 1u)) continue;                                            // warp-uniform
+            const float norm = softmax_numerators<CMAX, ACCURATE>(v, p.temp, p.scale);
+            if (id < 0) continue;
+            const uint32_t bits = inf & ~kGroupBit;
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c) v[c] = (EXACT || c < C) ? __ldcs(base + (size_t)c * P) : -INFINITY;
-            softmax_inplace<CMAX, ACCURATE>(v, p.temp, p.scale);
-            if (p.do_choice) {
-                float pos = 0.f;
-#pragma unroll
-                for (int c = 0; c < CMAX; ++c) pos += ((bits >> c) & 1u) ? v[c] : 0.f;
+            for (int c = 0; c < CMAX; ++c) {
+                if (EXACT || c < C) pst[c * kThreads] = v[c];
+            }
+            const bool group = do_group && (inf & kGroupBit) && bits != 0u;
+            if (group && id != cur) {
+                if (cur >= 0) {
+                    for (int c = 0; c < C; ++c) {
+                        const unsigned long long e = col[c * kThreads];
+                        if (e != 0ull) { atomicMax(p.gmax + cur_base + c, e); col[c * kThreads] = 0ull; }
+                    }
+                }
+                cur = id;
+                cur_base = ((long long)t.img * p.S + cur) * C;
+            }
+            // candidate classes in ascending order: probability mass and running maxima
+            const unsigned long long low = (unsigned long long)(~(uint32_t)(off0 + (size_t)r * p.W));
+            float pos = 0.f;
+            for (uint32_t b = bits; b; b &= b - 1u) {
+                const int c = __ffs(b) - 1;
+                const float pc = normalised<ACCURATE>(pst[c * kThreads], norm);
+                pos += pc;
+                if (group) {
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(pc) << 32) | low;
+                    if (key > col[c * kThreads]) col[c * kThreads] = key;
+                }
+            }
+            if (do_choice) {
                 const float l = -logf(pos + kEps);
                 const int n = __popc(bits);
                 if (n == 1) { sum_one += l; ++n_one; }
                 else if (n > 1) { sum_multi += l; ++n_multi; }
                 else { sum_empty += l; ++n_empty; }
             }
-            if (group) {
-                if (id != cur) {
-                    if (cur >= 0) {
-                        for (int c = 0; c < C; ++c) {
-                            const unsigned long long e = col[c * kThreads];
-                            if (e != 0ull) { atomicMax(p.gmax + cur_base + c, e); col[c * kThreads] = 0ull; }
-                        }
-                    }
-                    cur = id;
-                    cur_base = ((long long)t.img * p.S + id) * C;
-                }
-                const unsigned long long low = (unsigned long long)(~(uint32_t)off);
-#pragma unroll
-                for (int c = 0; c < CMAX; ++c) {
-                    if ((bits >> c) & 1u) {
-                        const unsigned long long key = ((unsigned long long)__float_as_uint(v[c]) << 32) | low;
-                        if (key > col[c * kThreads]) col[c * kThreads] = key;
-                    }
-                }
-            }
         }
         if (cur >= 0) {
             for (int c = 0; c < C; ++c) {
                 const unsigned long long e = col[c * kThreads];
-                if (e != 0ull) atomicMax(p.gmax + cur_base + c, e);
+                if (e != 0ull) { atomicMax(p.gmax + cur_base + c, e); col[c * kThreads] = 0ull; }
             }
         }
     }
 
-    if (p.do_choice) {
-        __shared__ float s_sum[3];
-        __shared__ int s_cnt[3];
-        if (tid < 3) { s_sum[tid] = 0.f; s_cnt[tid] = 0; }
-        __syncthreads();
+    if (do_choice) {      // one combine per CTA of the persistent grid, in a fixed order (run-to-run identical partials)
+        __shared__ float s_sum[kThreads / 32][3];
+        __shared__ int s_cnt[kThreads / 32][3];
         float s[3] = {sum_one, sum_multi, sum_empty};
         int n[3] = {n_one, n_multi, n_empty};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
-                n[k] += __shfl_xor_sync(0xffffffffu, n[k], o);
+                s[k] += __shfl_xor_sync(kFullWarp, s[k], o);
+                n[k] += __shfl_xor_sync(kFullWarp, n[k], o);
             }
-            if (lane == 0 && n[k] != 0) { atomicAdd(&s_sum[k], s[k]); atomicAdd(&s_cnt[k], n[k]); }
+            if (lane == 0) { s_sum[tid >> 5][k] = s[k]; s_cnt[tid >> 5][k] = n[k]; }
         }
         __syncthreads();
-        if (tid < 3 && s_cnt[tid] != 0) {
-            atomicAdd(p.acc + 2 * tid, (double)s_sum[tid]);
-            atomicAdd(p.acc + 2 * tid + 1, (double)s_cnt[tid]);
+        if (tid < 3) {
+            double total = 0.0;
+            long long count = 0;
+            for (int w = 0; w < kThreads / 32; ++w) { total += (double)s_sum[w][tid]; count += s_cnt[w][tid]; }
+            if (count != 0) {
+                atomicAdd(p.acc + 2 * tid, total);
+                atomicAdd(p.acc + 2 * tid + 1, (double)count);
+            }
         }
     }
 }
@@ -252,78 +368,168 @@ __global__ void group_loss_reduce_kernel(const unsigned long long* __restrict__ 
 // ------------------------------------------------------------------------------------------ backward
 template <int CMAX, bool EXACT, typename IdT>
 __global__ void __launch_bounds__(kThreads) multihot_loss_bwd_kernel(const LossParams p) {
+    extern __shared__ float pst_all[];     // [C][kThreads] softmax numerators of the pixel being processed
     const int C = EXACT ? CMAX : p.C;
-    const Tile t = my_tile(p);
-    if (!t.in_range || t.x >= p.W) return;
+    float* pst = pst_all + threadIdx.x;
+    const bool do_choice = p.do_choice != 0, do_group = p.do_group != 0;
     const float w_one = p.coef[0] * p.inv_temp, w_multi = p.coef[1] * p.inv_temp, w_group = p.coef[3] * p.inv_temp;
     const size_t P = (size_t)p.H * p.W;
-    for (int y = t.y0; y < t.y1; ++y) {
-        const size_t off = (size_t)y * p.W + t.x;
-        const size_t pix = (size_t)t.img * P + off;
-        float* gbase = p.grad + (size_t)t.img * C * P + off;
-        int id = -1;
-        uint32_t inf = 0u;
-        if (__ldcs(p.mask + pix) != 0) {
-            id = load_id<IdT>(p.ids, pix);
-            if ((unsigned)id < (unsigned)p.S) inf = __ldg(p.info + (size_t)t.img * p.S + id); else id = -1;
+    const long long n_tiles = tile_count(p);
+    const long long warp_stride = (long long)gridDim.x * (kThreads / 32);
+    for (long long tile = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += warp_stride) {
+        const Tile t = make_tile(p, tile);
+        const bool active = t.x < p.W;
+        const size_t off0 = (size_t)t.y0 * p.W + t.x;
+        const uint32_t mbits = tile_mask_bits(p, t, (size_t)t.img * P + off0);
+        if (tile + warp_stride < n_tiles) {
+            const Tile tn = make_tile(p, tile + warp_stride);
+            prefetch_tile_mask(p, tn, (size_t)tn.img * P + (size_t)tn.y0 * p.W + tn.x);
         }
-        const uint32_t bits = inf & ~kGroupBit;
-        const bool group = p.do_group && (inf & kGroupBit) && bits != 0u;
-        if (id < 0 || (!group && !(p.do_choice && bits != 0u))) {      // no gradient reaches this pixel
-            for (int c = 0; c < C; ++c) __stcs(gbase + (size_t)c * P, 0.f);
-            continue;
-        }
-        float v[CMAX];
-        const float* base = p.logits + (size_t)t.img * C * P + off;
+        const uint32_t any_rows = __reduce_or_sync(kFullWarp, mbits);
+        float* tgrad = p.grad + (size_t)t.img * C * P + off0;
+        if (any_rows == 0u) {          // warp-uniform: nothing selected in the tile -> independent streaming zero stores
+            if (active) {
+#pragma unroll 2
+                for (int r = 0; r < t.rows; ++r) {
+                    float* ptr = tgrad + (size_t)r * p.W;
 #pragma unroll
-        for (int c = 0; c < CMAX; ++c) v[c] = (EXACT || c < C) ? __ldcs(base + (size_t)c * P) : -INFINITY;
-        softmax_inplace<CMAX, false>(v, p.temp, p.scale);
-        float pos = 0.f;
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c) pos += ((bits >> c) & 1u) ? v[c] : 0.f;
-        float a = 0.f;
-        if (p.do_choice) {
-            const int n = __popc(bits);
-            a = -(n == 1 ? w_one : w_multi) / (pos + kEps);
-        }
-        uint32_t abits = 0u;   // classes whose max-pooled probability comes from this pixel
-        float q_sum = 0.f;
-        if (group) {
-            const uint32_t low = ~(uint32_t)off;
-            const unsigned long long* row = p.gmax + ((long long)t.img * p.S + id) * C;
-#pragma unroll
-            for (int c = 0; c < CMAX; ++c) {
-                if ((bits >> c) & 1u) {
-                    const unsigned long long e = __ldg(row + c);
-                    if ((uint32_t)e == low && (e >> 32) != 0ull) {
-                        abits |= 1u << c;
-                        q_sum += v[c] / (v[c] + kEps);
+                    for (int c = 0; c < CMAX; ++c) {
+                        if (EXACT || c < C) __stcs(ptr, 0.f);
+                        ptr += P;
                     }
                 }
             }
+            continue;
         }
+        RowPipe<CMAX, EXACT, IdT> pipe(p);
+        pipe.start(t, C, P, off0, mbits);
+#pragma unroll 1
+        for (int r = 0; r < kTileRows; ++r) {
+            float v[CMAX];
+            int id;
+            uint32_t inf;
+            pipe.next(v, id, inf);
+            const uint32_t bits = inf & ~kGroupBit;
+            const bool group = do_group && (inf & kGroupBit) && bits != 0u;
+            const bool live = id >= 0 && (group || (do_choice && bits != 0u));     // does any gradient reach this pixel?
+            const bool any_live = __any_sync(kFullWarp, live);
+            if (!active || r >= t.rows) continue;
+            float* gbase = tgrad + (size_t)r * p.W;
+            if (!any_live) {
+                float* ptr = gbase;
 #pragma unroll
-        for (int c = 0; c < CMAX; ++c) {
-            const float pc = v[c];
-            float g = a * pc * ((((bits >> c) & 1u) ? 1.f : 0.f) - pos);
-            if (abits) g -= w_group * ((((abits >> c) & 1u) ? pc / (pc + kEps) : 0.f) - pc * q_sum);
-            if (EXACT || c < C) __stcs(gbase + (size_t)c * P, g);
+                for (int c = 0; c < CMAX; ++c) {
+                    if (EXACT || c < C) __stcs(ptr, 0.f);
+                    ptr += P;
+                }
+                continue;
+            }
+            const float inv = softmax_numerators<CMAX, false>(v, p.temp, p.scale);
+            // d/dx_c = P_c * (a * ([c in row] - pos) + w_group * q_sum) - w_group * [c pooled from this pixel] * q_c
+            // with q_c = P_c / (P_c + eps).  Hardly any pixel is the arg-max pixel of a max-pool: those entries are patched.
+            float s_in = 0.f, s_out = 0.f;
+            uint32_t abits = 0u;   // classes whose max-pooled probability comes from this pixel
+            if (live) {
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) {
+                    if (EXACT || c < C) pst[c * kThreads] = v[c];
+                }
+                const uint32_t low = ~(uint32_t)(off0 + (size_t)r * p.W);
+                // the table entry holds ~pixel in its low word (an empty entry holds 0, which no pixel maps to)
+                const uint32_t* row = reinterpret_cast<const uint32_t*>(p.gmax + ((long long)t.img * p.S + id) * C);
+                float pos = 0.f, q_sum = 0.f;
+                for (uint32_t b = bits; b; b &= b - 1u) {
+                    const int c = __ffs(b) - 1;
+                    const float pc = pst[c * kThreads] * inv;
+                    pos += pc;
+                    if (group && __ldg(row + 2 * c) == low) {
+                        abits |= 1u << c;
+                        q_sum += __fdividef(pc, pc + kEps);
+                    }
+                }
+                float a = 0.f;
+                if (do_choice) a = -(__popc(bits) == 1 ? w_one : w_multi) / (pos + kEps);
+                const float shared_term = abits ? w_group * q_sum : 0.f;
+                s_in = (a * (1.f - pos) + shared_term) * inv;
+                s_out = (shared_term - a * pos) * inv;
+            }
+            {
+                float* ptr = gbase;
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) {
+                    const float gr = v[c] * (((bits >> c) & 1u) ? s_in : s_out);
+                    if (EXACT || c < C) __stcs(ptr, live ? gr : 0.f);
+                    ptr += P;
+                }
+            }
+            for (uint32_t b = abits; b; b &= b - 1u) {       // rare: this pixel owns a max-pooled probability
+                const int c = __ffs(b) - 1;
+                const float e = pst[c * kThreads];
+                const float pc = e * inv;
+                __stcs(gbase + (size_t)c * P, e * s_in - w_group * __fdividef(pc, pc + kEps));
+            }
         }
     }
 }
 
+// losses[0] one-hot CE            s0 / (1 + n0)
+// losses[1] multi-hot, strict     s1 / (1 + n1)                        (active_joint_multi_lossdecomp.py:67-72)
+// losses[2] multi-hot := not one  (s1 + s2) / (1 + n1 + n2)            (..._predignore_lossdecomp.py:65-70)
+// losses[3] multi-choice          (s0 + s1) / (1 + n0 + n1)            (utils/loss.py:572-588, empty rows dropped)
+// losses[4] group / MIL           s3 / (1 + n3)                        (utils/loss.py:131-141)
+// fp32 sums divided by fp32 counters, like the reference's `loss / num_valid`
+__global__ void loss_finish_kernel(const double* __restrict__ acc, float* __restrict__ losses) {
+    if (threadIdx.x != 0) return;
+    const float s0 = (float)acc[0], s1 = (float)acc[2], s2 = (float)acc[4], s3 = (float)acc[6];
+    const double n0 = acc[1], n1 = acc[3], n2 = acc[5], n3 = acc[7];
+    losses[0] = s0 / (float)(1.0 + n0);
+    losses[1] = s1 / (float)(1.0 + n1);
+    losses[2] = (s1 + s2) / (float)(1.0 + n1 + n2);
+    losses[3] = (s0 + s1) / (float)(1.0 + n0 + n1);
+    losses[4] = s3 / (float)(1.0 + n3);
+    losses[5] = 0.f;
+}
+
+// coef[k] = d (sum_j grad[j] * losses[j]) / d (bucket sum k)
+__global__ void loss_coef_kernel(const double* __restrict__ acc, const float* __restrict__ grad, float* __restrict__ coef) {
+    if (threadIdx.x != 0) return;
+    const double n0 = acc[1], n1 = acc[3], n2 = acc[5], n3 = acc[7];
+    const float d0 = (float)(1.0 + n0), d1 = (float)(1.0 + n1), d12 = (float)(1.0 + n1 + n2), d01 = (float)(1.0 + n0 + n1);
+    coef[0] = grad[0] / d0 + grad[3] / d01;
+    coef[1] = grad[1] / d1 + grad[2] / d12 + grad[3] / d01;
+    coef[2] = grad[2] / d12;
+    coef[3] = grad[4] / (float)(1.0 + n3);
+}
+
 // ------------------------------------------------------------------------------------------ launch
+template <typename K>
+int resident_ctas(K kernel, size_t smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+
 template <int CMAX, bool EXACT, typename IdT>
 cudaError_t launch_one(const LossParams& p, bool backward, bool accurate, cudaStream_t stream) {
     const long long tiles = (long long)p.n_img * ((p.W + 31) / 32) * ((p.H + kTileRows - 1) / kTileRows);
-    const long long blocks = (tiles + kThreads / 32 - 1) / (kThreads / 32);
-    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const long long want = (tiles + kThreads / 32 - 1) / (kThreads / 32);
+    // forward: running maxima (u64) + softmax numerators (f32) per (class, thread); backward: the numerators
+    const size_t smem = (size_t)p.C * kThreads * (backward ? sizeof(float) : sizeof(unsigned long long) + sizeof(float));
+    // persistent grid: one wave of resident CTAs (per instantiation; the generic channel padding changes smem by < 2x)
+    static int per_sm[3] = {0, 0, 0};
+    const int which = backward ? 0 : (accurate ? 1 : 2);
+    if (per_sm[which] == 0) {
+        const size_t smem_max = (size_t)CMAX * kThreads * (backward ? sizeof(float) : sizeof(unsigned long long) + sizeof(float));
+        if (backward) per_sm[which] = resident_ctas(multihot_loss_bwd_kernel<CMAX, EXACT, IdT>, smem_max);
+        else if (accurate) per_sm[which] = resident_ctas(multihot_loss_fwd_kernel<CMAX, EXACT, IdT, true>, smem_max);
+        else per_sm[which] = resident_ctas(multihot_loss_fwd_kernel<CMAX, EXACT, IdT, false>, smem_max);
+    }
+    const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)mas::sm_count() * per_sm[which]));
     if (backward) {
-        multihot_loss_bwd_kernel<CMAX, EXACT, IdT><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+        multihot_loss_bwd_kernel<CMAX, EXACT, IdT><<<blocks, kThreads, smem, stream>>>(p);
     } else {
-        const size_t smem = p.do_group ? (size_t)p.C * kThreads * sizeof(unsigned long long) : 0;
-        if (accurate) multihot_loss_fwd_kernel<CMAX, EXACT, IdT, true><<<(unsigned)blocks, kThreads, smem, stream>>>(p);
-        else multihot_loss_fwd_kernel<CMAX, EXACT, IdT, false><<<(unsigned)blocks, kThreads, smem, stream>>>(p);
+        if (accurate) multihot_loss_fwd_kernel<CMAX, EXACT, IdT, true><<<blocks, kThreads, smem, stream>>>(p);
+        else multihot_loss_fwd_kernel<CMAX, EXACT, IdT, false><<<blocks, kThreads, smem, stream>>>(p);
     }
     mas::count_launches(1);
     return cudaGetLastError();
@@ -425,5 +631,21 @@ extern "C" int mas_multihot_loss_bwd_dev(const float* logits, const void* ids, i
     p.coef = coef; p.grad = grad_logits;
     cudaError_t e = dispatch(p, ids_dtype, true, false, (cudaStream_t)stream);
     if (e != cudaSuccess) return mas::cuda_fail(e, "multihot_loss_bwd_kernel launch");
+    return 0;
+}
+
+extern "C" int mas_multihot_loss_finish_dev(const double* acc, float* losses, void* stream) {
+    MAS_REQUIRE(acc && losses, MAS_E_BADARG, "multihot_loss_finish: null pointer");
+    loss_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, losses);
+    mas::count_launches(1);
+    MAS_LAUNCH_OK("loss_finish_kernel");
+    return 0;
+}
+
+extern "C" int mas_multihot_loss_coef_dev(const double* acc, const float* grad_losses, float* coef, void* stream) {
+    MAS_REQUIRE(acc && grad_losses && coef, MAS_E_BADARG, "multihot_loss_coef: null pointer");
+    loss_coef_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, grad_losses, coef);
+    mas::count_launches(1);
+    MAS_LAUNCH_OK("loss_coef_kernel");
     return 0;
 }

@@ -29,10 +29,11 @@ from torch import nn
 from . import _lib, ops
 
 
-# Forward softmax in the reference's operation order (x / T, max-subtract, expf, divide by the sum) rather than the fast
-# ex2 / reciprocal form: a few hundred extra instructions per SELECTED pixel, invisible at the labelled fractions of a
-# real round; set to False to trade the last bits of parity for speed when every pixel is labelled.
-EXACT_SOFTMAX = True
+# Forward softmax in the reference's operation order (x / T, max-subtract, expf, divide by the sum) instead of the fast
+# ex2 / reciprocal form (<= 4 ulp apart, both far inside the 1e-5 tolerance of the losses).  The exact form costs several
+# hundred extra instructions per SELECTED pixel and makes the forward kernel issue-bound when most pixels are labelled;
+# the stage-2 labeller, where the arg-max PIXEL must agree with torch on near-ties, always uses it.
+EXACT_SOFTMAX = False
 
 
 class _SegmentedLossSums(torch.autograd.Function):
@@ -59,6 +60,48 @@ class _SegmentedLossSums(torch.autograd.Function):
         return grad, None, None, None, None, None, None
 
 
+class _SegmentedLosses(torch.autograd.Function):
+    """The same fused pass as ``_SegmentedLossSums`` with the reference's normalisations folded in on the device:
+    returns the six 0-dim losses of ``mas_multihot_loss_finish_dev`` (views of one (6,) tensor) and the bucket
+    counts (4,) f64.  A step is 5 launches forward (zero-fill, candidate words, fused pass, group reduce, finish)
+    and 3 backward (stack of the incoming gradients, coefficients, fused pass)."""
+
+    @staticmethod
+    def forward(ctx, inputs, spx, mask, info, nseg, temperature, flags):
+        x = inputs.contiguous()
+        acc, gmax = ops.multihot_loss_forward(x, spx, mask, info, nseg, temperature, flags)
+        losses = ops.multihot_loss_finish(acc)
+        ctx.save_for_backward(x, spx, mask, info, acc, gmax if gmax is not None else torch.empty(0, device=x.device))
+        ctx.nseg, ctx.temperature, ctx.flags = nseg, temperature, flags
+        ctx.set_materialize_grads(False)
+        counts = acc[1::2]
+        ctx.mark_non_differentiable(counts)
+        return (*losses.unbind(0), counts)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x, spx, mask, info, acc, gmax = ctx.saved_tensors
+        grads = grads[:6]
+        if all(g is None for g in grads):
+            return (None,) * 7
+        zero = None
+        parts = []
+        for g in grads:
+            if g is None:
+                if zero is None:
+                    zero = torch.zeros((), dtype=torch.float32, device=x.device)
+                g = zero
+            parts.append(g.to(torch.float32).reshape(()))
+        coef = ops.multihot_loss_coef(acc, torch.stack(parts))
+        grad = ops.multihot_loss_backward(x, spx, mask, info, gmax if gmax.numel() else None, coef, ctx.nseg,
+                                          ctx.temperature, ctx.flags & ~_lib.MAS_LOSS_EXACT_SOFTMAX)
+        return grad, None, None, None, None, None, None
+
+
+# positions in the tuple returned by ``segmented_losses``
+ONE_HOT, MULTI_STRICT, MULTI_NOT_ONE, CHOICE_ALL, GROUP, COUNTS = 0, 1, 2, 3, 4, 6
+
+
 def _prepare(inputs, targets, superpixels, spmasks):
     if not inputs.is_cuda:
         raise RuntimeError("mulactseg_b200 losses need CUDA tensors (there is no CPU path)")
@@ -82,6 +125,18 @@ def segmented_loss_sums(inputs, targets, superpixels, spmasks, temperature: floa
     if EXACT_SOFTMAX:
         flags |= _lib.MAS_LOSS_EXACT_SOFTMAX
     return _SegmentedLossSums.apply(inputs, spx, mask, info, nseg, float(temperature), flags)
+
+
+def segmented_losses(inputs, targets, superpixels, spmasks, temperature: float, group_mode: Optional[int], want_choice: bool):
+    """Like ``segmented_loss_sums`` but normalised on the device: -> tuple indexed by ONE_HOT .. GROUP (0-dim losses)
+    and COUNTS ((4,) f64 bucket counts)."""
+    trg, spx, mask = _prepare(inputs, targets, superpixels, spmasks)
+    nseg = trg.shape[1]
+    info = ops.multihot_info(trg, inputs.shape[1], _lib.MAS_GROUP_ALL if group_mode is None else group_mode)
+    flags = (_lib.MAS_LOSS_CHOICE if want_choice else 0) | (_lib.MAS_LOSS_GROUP if group_mode is not None else 0)
+    if EXACT_SOFTMAX:
+        flags |= _lib.MAS_LOSS_EXACT_SOFTMAX
+    return _SegmentedLosses.apply(inputs, spx, mask, info, nseg, float(temperature), flags)
 
 
 class SharedPass:
@@ -123,7 +178,7 @@ class SharedPass:
         wanted = self._wanted(module.temp)
         if wanted is None:
             wanted = (module.group_mode, module.wants_choice)
-        value = segmented_loss_sums(inputs, targets, superpixels, spmasks, module.temp, wanted[0], wanted[1])
+        value = segmented_losses(inputs, targets, superpixels, spmasks, module.temp, wanted[0], wanted[1])
         # identity through weak references: a recycled id() of a dead tensor can never hit the cache
         self._refs = tuple(weakref.ref(t) for t in tensors)
         self._key, self._value = key, (wanted[0], wanted[1], value)
@@ -146,10 +201,10 @@ class _SegmentedLoss(nn.Module):
         shared.register(self)
         return self
 
-    def _sums(self, inputs, targets, superpixels, spmasks):
+    def _losses(self, inputs, targets, superpixels, spmasks):
         if self.shared is not None:
             return self.shared.sums(self, inputs, targets, superpixels, spmasks)
-        return segmented_loss_sums(inputs, targets, superpixels, spmasks, self.temp, self.group_mode, self.wants_choice)
+        return segmented_losses(inputs, targets, superpixels, spmasks, self.temp, self.group_mode, self.wants_choice)
 
 
 class GroupMultiLabelCE(_SegmentedLoss):
@@ -163,12 +218,11 @@ class GroupMultiLabelCE(_SegmentedLoss):
         self.num_superpixel = num_superpixel
 
     def forward(self, inputs, targets, superpixels, spmasks):
-        sums, counts = self._sums(inputs, targets, superpixels, spmasks)
-        num_valid = 1 + counts[3]
         if self.reduction == "mean":
-            return sums[3] / num_valid.to(torch.float32)
-        if self.reduction == "none":
-            return sums[3], num_valid
+            return self._losses(inputs, targets, superpixels, spmasks)[GROUP]
+        if self.reduction == "none":                     # (loss sum, num_valid), utils/loss.py:137-139
+            sums, counts = segmented_loss_sums(inputs, targets, superpixels, spmasks, self.temp, self.group_mode, False)
+            return sums[3], 1 + counts[3]
         raise NotImplementedError
 
 
@@ -192,8 +246,7 @@ class MultiChoiceCE(_SegmentedLoss):
     def forward(self, inputs, targets, superpixels, spmasks):
         if self.reduction != "mean":
             raise NotImplementedError("only reduction='mean' (what the shipped recipes use) is provided")
-        sums, counts = self._sums(inputs, targets, superpixels, spmasks)
-        return (sums[0] + sums[1]) / (1 + counts[0] + counts[1]).to(torch.float32)
+        return self._losses(inputs, targets, superpixels, spmasks)[CHOICE_ALL]
 
 
 class MultiChoiceCE_(MultiChoiceCE):
@@ -215,13 +268,12 @@ class OnehotCEMultihotChoice(MultiChoiceCE):
         self.assert_partition = assert_partition
 
     def forward(self, inputs, targets, superpixels, spmasks):
-        sums, counts = self._sums(inputs, targets, superpixels, spmasks)
-        one = sums[0] / (1 + counts[0]).to(torch.float32)
+        out = self._losses(inputs, targets, superpixels, spmasks)
         if self.strict_multihot:
-            return one, sums[1] / (1 + counts[1]).to(torch.float32)
+            return out[ONE_HOT], out[MULTI_STRICT]
         if self.assert_partition:
-            assert float(counts[2]) == 0.0   # ..._lossdecomp.py:67
-        return one, (sums[1] + sums[2]) / (1 + counts[1] + counts[2]).to(torch.float32)
+            assert float(out[COUNTS][2]) == 0.0   # ..._lossdecomp.py:67
+        return out[ONE_HOT], out[MULTI_NOT_ONE]
 
 
 class OnehotCEMultihotChoiceVOC(OnehotCEMultihotChoice):

@@ -200,8 +200,11 @@ def multihot_loss_forward(logits: torch.Tensor, spx: torch.Tensor, mask: torch.T
                           temperature: float, flags: int):
     """-> (acc (8,) f64 bucket sums / counts, group_max (N,nseg,C) i64 packed maxima or None)."""
     n, c, h, w = _loss_args(logits, spx, mask, info, nseg)
-    acc = torch.zeros(8, dtype=torch.float64, device=logits.device)
-    gmax = torch.zeros((n, nseg, c), dtype=torch.int64, device=logits.device) if flags & _lib.MAS_LOSS_GROUP else None
+    # one zero-fill for both: 8 accumulators (viewed as f64) followed by the max-pool table
+    want_group = bool(flags & _lib.MAS_LOSS_GROUP)
+    buf = torch.zeros(8 + (n * nseg * c if want_group else 0), dtype=torch.int64, device=logits.device)
+    acc = buf[:8].view(torch.float64)
+    gmax = buf[8:].view(n, nseg, c) if want_group else None
     with torch.cuda.device(logits.device):
         _lib.call("mas_multihot_loss_fwd_dev", logits.data_ptr(), spx.data_ptr(), _ids_dtype(spx), mask.data_ptr(),
                   info.data_ptr(), n, c, h, w, int(nseg), float(temperature), int(flags), acc.data_ptr(), _ptr(gmax),
@@ -223,6 +226,27 @@ def multihot_loss_backward(logits: torch.Tensor, spx: torch.Tensor, mask: torch.
                   info.data_ptr(), _ptr(gmax), coef.data_ptr(), n, c, h, w, int(nseg), float(temperature), int(flags),
                   grad.data_ptr(), _stream(logits))
     return grad
+
+
+def multihot_loss_finish(acc: torch.Tensor) -> torch.Tensor:
+    """(8,) f64 bucket sums / counts -> (6,) f32 normalised losses (see ``mas_multihot_loss_finish_dev``)."""
+    _want(acc, "acc", torch.float64, 1)
+    losses = torch.empty(6, dtype=torch.float32, device=acc.device)
+    with torch.cuda.device(acc.device):
+        _lib.call("mas_multihot_loss_finish_dev", acc.data_ptr(), losses.data_ptr(), _stream(acc))
+    return losses
+
+
+def multihot_loss_coef(acc: torch.Tensor, grad_losses: torch.Tensor) -> torch.Tensor:
+    """Gradient of the 6 normalised losses folded back onto the 4 bucket sums (device floats)."""
+    _want(acc, "acc", torch.float64, 1)
+    _want(grad_losses, "grad_losses", torch.float32, 1)
+    if grad_losses.numel() != 6:
+        raise RuntimeError("grad_losses must hold 6 floats")
+    coef = torch.empty(4, dtype=torch.float32, device=acc.device)
+    with torch.cuda.device(acc.device):
+        _lib.call("mas_multihot_loss_coef_dev", acc.data_ptr(), grad_losses.data_ptr(), coef.data_ptr(), _stream(acc))
+    return coef
 
 
 # ------------------------------------------------------------------------------------------------ stage-2 labellers

@@ -68,6 +68,35 @@ def test_proto_labeller_matches_oracle(shape, only_multihot, thr):
     assert mismatch == 0, f"{mismatch} of {h * w} pixels differ"
 
 
+def test_voc_multiscale_variant_matches_oracle():
+    """..._includeonehot_voc_ms.py: features averaged over scales (+ flipped copies) and re-normalised, then the same
+    pseudo_label_generation; VOC-shaped (21 classes, ~150 superpixels)."""
+    import types
+    from mulactseg_b200.trainer import eval_save_cosplbl_prop_includeonehot_voc_ms as ms
+    h, w, nseg, c, ch = 60, 84, 24, 21, 32
+    scales = [(30, 42), (60, 84), (90, 126)]
+    feat_list, out_list = [], []
+    for k, (hk, wk) in enumerate(scales + scales):              # second half: computed on flipped images
+        f = synth.features(1, ch, hk * 4, wk * 4, seed=10 + k)[:, :, ::4, ::4].contiguous()
+        o = synth.logits(1, c, hk, wk, "normal", seed=20 + k, coherent=2)
+        feat_list.append(f)
+        out_list.append(o)
+    feats, logits = ms.fuse_multiscale(feat_list, out_list, (h, w))
+    assert feats.shape == (1, ch, h, w) and logits.shape == (1, c, h, w)
+    np.testing.assert_allclose(feats.norm(dim=1).numpy(), 1.0, rtol=1e-5)
+    spx = synth.superpixel_map(1, h, w, nseg, "jitter", seed=3)
+    trg = synth.multihot_targets(1, nseg, c, seed=4, p_extra=0.15)
+    mask = synth.region_mask(spx, nseg, 0.4, seed=5)
+    ref = ol.pseudo_label_generation(feats, logits, trg, mask, spx, only_multihot=False, threshold="median")
+
+    class Trainer(ms.LabellerMixin):
+        args = types.SimpleNamespace(nseg=nseg, cosprop_threshold_method="median")
+
+    got = Trainer().pseudo_label_generation(torch.zeros_like(spx), feats.to(DEV), logits.to(DEV), trg.to(DEV), mask.to(DEV),
+                                            spx.to(DEV)).cpu()
+    assert int((got != ref).sum()) == 0
+
+
 def test_top_labeller_matches_oracle_and_quirk():
     from mulactseg_b200 import labeller
     n, c, h, w, nseg = 3, 9, 31, 45, 14

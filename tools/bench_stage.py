@@ -34,14 +34,16 @@ def peak():
     return json.load(open(path))["hbm_gbs"] if os.path.exists(path) else 6650.0
 
 
-def bench_losses(res, profile):
+def bench_losses(res, profile, only_rho=None, only_exact=None):
     dev = "cuda:0"
     n, c, h, w, nseg = 16, 20, 768, 768, 2048
     x = synth.logits(n, c, h, w, "cosine", seed=1, device=dev, coherent=4)
     spx = synth.pad_border(synth.superpixel_map(n, h, w, nseg, "jitter", seed=2, device=dev), nseg, 16)
     trg = synth.multihot_targets(n, nseg, c, seed=3, device=dev, p_ignore=0.0)
     args = types.SimpleNamespace(nseg=nseg, group_ce_temp=0.1, multi_ce_temp=0.1)
-    for rho, exact in ((0.02, True), (0.2, True), (1.0, True), (1.0, False)):
+    for rho, exact in ((0.02, False), (0.2, False), (1.0, False), (1.0, True)):
+        if (only_rho is not None and rho != only_rho) or (only_exact is not None and exact != bool(only_exact)):
+            continue
         losses.EXACT_SOFTMAX = exact
         mask = synth.region_mask(spx, nseg, rho, seed=4)
         group, multi = losses.stage1_criterion(args, c - 1)
@@ -104,10 +106,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--profile", action="store_true", help="few iterations (for ncu)")
     ap.add_argument("--only", default="", choices=["", "losses", "labeller"])
+    ap.add_argument("--rho", type=float, default=None, help="losses: only this labelled fraction")
+    ap.add_argument("--exact", type=int, default=None, help="losses: only this softmax mode (0 fast / 1 exact)")
     args = ap.parse_args()
     res = {}
     if args.only in ("", "losses"):
-        bench_losses(res, args.profile)
+        bench_losses(res, args.profile, args.rho, args.exact)
     if args.only in ("", "labeller"):
         bench_labeller(res, args.profile)
     os.makedirs("gpurun_out", exist_ok=True)
