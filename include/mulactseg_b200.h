@@ -139,6 +139,16 @@ int mas_topk_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, 
 int64_t mas_sort_capacity(int64_t n);
 int mas_sort_desc_u64_dev(uint64_t* keys, int64_t n, void* stream);
 
+/* mas_topk_sorted_u64_dev -- the same result as mas_topk_u64_dev followed by mas_sort_desc_u64_dev in 3 + sort launches:
+ * two histogram passes (key bits 63..52, then 51..40) locate the 24-bit prefix of the k-th largest key, one compaction
+ * pass keeps every key from that prefix upwards, the sort orders them.  `out` has `capacity` slots (a sort capacity >=
+ * mas_sort_capacity(k)) and is fully overwritten: out[0 .. count) = the count = min(k, #non-zero keys) largest keys in
+ * descending order.  *out_count = -1 when the candidates did not fit `capacity` (massively tied scores): call the
+ * exact two-step path instead.  workspace: mas_topk_workspace_bytes().
+ */
+int mas_topk_sorted_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int64_t capacity, int32_t* out_count,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ host-buffer entries (end-to-end)
  *
  * mas_acquisition_host -- the whole scoring pass of one selector with HOST buffers.  Streams

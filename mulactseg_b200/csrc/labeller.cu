@@ -313,7 +313,11 @@ __global__ void __launch_bounds__(kAssignThreads) proto_assign_kernel(LabelParam
 }
 
 // one CTA per selected superpixel: per-prototype threshold = lower median (torch.median) or min of the similarities of
-// the pixels assigned to it, 1.0 if none  (:241-255)
+// the pixels assigned to it, 1.0 if none  (:241-255).  The (similarity, class) pairs of the superpixel's selected pixels
+// are read once into registers (kHold per thread; larger superpixels re-read them from global memory in every pass);
+// each class then takes a count + 4 x 8-bit radix-select passes over them.
+constexpr int kHold = 8;
+
 __global__ void __launch_bounds__(kAssignThreads) proto_threshold_kernel(LabelParams p) {
     __shared__ unsigned int hist[256];
     __shared__ unsigned int sel_prefix, sel_rank;
@@ -323,6 +327,37 @@ __global__ void __launch_bounds__(kAssignThreads) proto_threshold_kernel(LabelPa
     const uint32_t inf = p.info[s];
     const uint32_t bits = inf & ~kGroupBit;
     const int beg = p.offset[s], end = p.offset[s + 1];
+    const bool held = end - beg <= kHold * kAssignThreads;
+    float hsim[kHold];
+    int hcls[kHold];       // -1: no selected pixel in this slot
+    if (held) {
+        int pix[kHold];
+#pragma unroll
+        for (int i = 0; i < kHold; ++i) {
+            const int e = beg + i * kAssignThreads + threadIdx.x;
+            pix[i] = e < end ? p.pixlist[e] : -1;
+        }
+#pragma unroll
+        for (int i = 0; i < kHold; ++i) {
+            const bool on = pix[i] >= 0 && pixel_selected(p, pix[i], inf);
+            hcls[i] = on ? (int)p.own_cls[pix[i]] : -1;
+            hsim[i] = on ? p.own_sim[pix[i]] : 0.f;
+        }
+    }
+    // visit(sim) for every selected pixel of s assigned to class c
+    auto for_each = [&](int c, auto visit) {
+        if (held) {
+#pragma unroll
+            for (int i = 0; i < kHold; ++i) {
+                if (hcls[i] == c) visit(hsim[i]);
+            }
+        } else {
+            for (int e = beg + threadIdx.x; e < end; e += blockDim.x) {
+                const int pix = p.pixlist[e];
+                if (pixel_selected(p, pix, inf) && p.own_cls[pix] == c) visit(p.own_sim[pix]);
+            }
+        }
+    };
     uint32_t b = bits;
     while (b) {
         const int c = __ffs(b) - 1;
@@ -330,10 +365,7 @@ __global__ void __launch_bounds__(kAssignThreads) proto_threshold_kernel(LabelPa
         float result;
         if (p.threshold_min) {
             float mn = INFINITY;
-            for (int e = beg + threadIdx.x; e < end; e += blockDim.x) {
-                const int pix = p.pixlist[e];
-                if (pixel_selected(p, pix, inf) && p.own_cls[pix] == c) mn = fminf(mn, p.own_sim[pix]);
-            }
+            for_each(c, [&](float sim) { mn = fminf(mn, sim); });
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
             if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mn;
@@ -352,13 +384,11 @@ __global__ void __launch_bounds__(kAssignThreads) proto_threshold_kernel(LabelPa
                 __syncthreads();
                 const uint32_t prefix = sel_prefix;
                 const int shift = pass < 0 ? 0 : 24 - 8 * pass;
-                for (int e = beg + threadIdx.x; e < end; e += blockDim.x) {
-                    const int pix = p.pixlist[e];
-                    if (!pixel_selected(p, pix, inf) || p.own_cls[pix] != c) continue;
-                    if (pass < 0) { atomicAdd(&hist[0], 1u); continue; }
-                    const uint32_t key = mas::ordered_bits(p.own_sim[pix]);
+                for_each(c, [&](float sim) {
+                    if (pass < 0) { atomicAdd(&hist[0], 1u); return; }
+                    const uint32_t key = mas::ordered_bits(sim);
                     if ((key & mask_bits) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-                }
+                });
                 __syncthreads();
                 if (pass < 0) {
                     const unsigned int n = hist[0];

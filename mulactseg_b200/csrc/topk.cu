@@ -93,9 +93,103 @@ __global__ void select_finish_kernel(const SelectState* st, int32_t* out_count, 
     *out_count = (int32_t)min((long long)st->out_count, k);
 }
 
+// ---------------------------------------------------------------------------------------- fast path: bucket + sort
+// Two histogram passes (key bits 63..52, then 51..40 inside the bucket of the k-th largest key) pin down the first 24
+// bits of the k-th key: sign, exponent and 15 mantissa bits of its score.  ONE compaction pass then keeps every key from
+// that prefix upwards -- k plus the few keys whose scores agree with the k-th to 3e-5 relative -- and the bitonic sort
+// that has to run anyway orders them.  If the candidates do not fit the sort buffer (massively tied scores) the caller
+// falls back to the exact 8-pass radix select above.
+constexpr int kFastBits = 12;
+constexpr int kFastBins = 1 << kFastBits;
+
+struct FastState {
+    unsigned int hist[2][kFastBins];
+    unsigned int ticket[2];
+    unsigned int count;            // candidates written (may exceed the capacity: overflow)
+    unsigned int take_all;         // fewer non-zero keys than k
+    long long remaining;           // rank of the k-th key inside the level-0 bucket (1-based)
+    unsigned long long thr;        // smallest key prefix kept
+};
+
+// level 0: histogram of key bits 63..52 over all non-zero keys; level 1: bits 51..40 over the keys of the level-0 bucket.
+// The last CTA to finish locates the bin holding the wanted rank and extends the threshold prefix.
+__global__ void __launch_bounds__(256) fast_hist_kernel(const unsigned long long* __restrict__ keys, long long n, FastState* st,
+                                                        long long k, int level) {
+    __shared__ unsigned int local[kFastBins];
+    __shared__ unsigned int part[256];
+    __shared__ bool last;
+    if (level == 1 && st->take_all) return;
+    const unsigned long long bucket = st->thr >> (64 - kFastBits);     // level 1 only
+    for (int i = threadIdx.x; i < kFastBins; i += 256) local[i] = 0u;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const unsigned long long key = keys[i];
+        if (key == 0ull) continue;
+        if (level == 0) atomicAdd(&local[(unsigned)(key >> (64 - kFastBits))], 1u);
+        else if ((key >> (64 - kFastBits)) == bucket) atomicAdd(&local[(unsigned)(key >> (64 - 2 * kFastBits)) & (kFastBins - 1)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kFastBins; i += 256) {
+        if (local[i]) atomicAdd(&st->hist[level][i], local[i]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&st->ticket[level], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    // thread t owns bins [16 t, 16 t + 16); walk from the top
+    constexpr int kPer = kFastBins / 256;
+    const long long want = level == 0 ? k : st->remaining;
+    unsigned int h[kPer];
+    unsigned int mine = 0u;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) { h[i] = __ldcg(&st->hist[level][threadIdx.x * kPer + i]); mine += h[i]; }
+    part[threadIdx.x] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {          // suffix sums over 256 partials
+        unsigned int run = 0u;
+        for (int t = 255; t >= 0; --t) { const unsigned int v = part[t]; part[t] = run; run += v; }
+        if ((long long)run < want) { st->take_all = 1u; st->thr = 1ull; }      // (level 0 only) keep every non-zero key
+    }
+    __syncthreads();
+    long long above = part[threadIdx.x];                  // keys in bins above this thread's range
+#pragma unroll
+    for (int i = kPer - 1; i >= 0; --i) {
+        if (above < want && above + (long long)h[i] >= want) {
+            const unsigned long long bin = (unsigned long long)(threadIdx.x * kPer + i);
+            if (level == 0) { st->thr = bin << (64 - kFastBits); st->remaining = want - above; }
+            else st->thr |= bin << (64 - 2 * kFastBits);
+        }
+        above += h[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) fast_compact_kernel(const unsigned long long* __restrict__ keys, long long n, FastState* st,
+                                                           unsigned long long* __restrict__ out, long long capacity) {
+    const unsigned long long thr = max(st->thr, 1ull);
+    const int lane = threadIdx.x & 31;
+    const long long padded = (n + 31) & ~31ll;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < padded; i += (long long)gridDim.x * 256) {
+        const unsigned long long key = i < n ? keys[i] : 0ull;
+        const bool keep = key >= thr;
+        const unsigned int votes = __ballot_sync(0xffffffffu, keep);
+        if (votes == 0u) continue;
+        unsigned int base = 0u;
+        if (lane == __ffs(votes) - 1) base = atomicAdd(&st->count, (unsigned int)__popc(votes));
+        base = __shfl_sync(0xffffffffu, base, __ffs(votes) - 1);
+        const long long slot = (long long)base + __popc(votes & ((1u << lane) - 1u));
+        if (keep && slot < capacity) out[slot] = key;
+    }
+}
+
+__global__ void fast_finish_kernel(const FastState* st, int32_t* out_count, long long k, long long capacity) {
+    const long long c = st->count;
+    *out_count = c > capacity ? -1 : (int32_t)min(c, k);
+}
+
 // ---------------------------------------------------------------------------------------- bitonic sort (descending)
 constexpr int kSortThreads = 1024;
-constexpr int kSortTile = 2 * kSortThreads;
+constexpr int kSortTile = 8192;            // keys per CTA: 64 KB of shared memory, 4 comparators per thread and step
 
 __device__ __forceinline__ void cmp_swap_desc(unsigned long long& a, unsigned long long& b, bool descending) {
     if ((a < b) == descending) { const unsigned long long t = a; a = b; b = t; }
@@ -106,25 +200,37 @@ __global__ void sort_pad_kernel(unsigned long long* keys, long long n, long long
     if (i < n_pad) keys[i] = 0ull;
 }
 
-// sort each tile of kSortTile keys; tile t is sorted descending if bit (t & 1) == 0 else ascending
-__global__ void __launch_bounds__(kSortThreads) sort_tile_kernel(unsigned long long* keys) {
-    __shared__ unsigned long long s[kSortTile];
-    unsigned long long* g = keys + (long long)blockIdx.x * kSortTile;
-    s[threadIdx.x] = g[threadIdx.x];
-    s[threadIdx.x + kSortThreads] = g[threadIdx.x + kSortThreads];
-    for (int k = 2; k <= kSortTile; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            __syncthreads();
-            const int i = 2 * threadIdx.x - (threadIdx.x & (j - 1));
-            const long long gi = (long long)blockIdx.x * kSortTile + i;
-            cmp_swap_desc(s[i], s[i + j], (gi & k) == 0);
+// strides j_from .. 1 of stage k inside the tile held in shared memory
+__device__ __forceinline__ void tile_steps(unsigned long long* s, long long tile_base, long long k, int j_from) {
+    for (int j = j_from; j > 0; j >>= 1) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < kSortTile / 2; c += kSortThreads) {
+            const int i = 2 * c - (c & (j - 1));
+            cmp_swap_desc(s[i], s[i + j], ((tile_base + i) & k) == 0);
         }
     }
     __syncthreads();
-    g[threadIdx.x] = s[threadIdx.x];
-    g[threadIdx.x + kSortThreads] = s[threadIdx.x + kSortThreads];
 }
 
+// sort each tile of kSortTile keys (stages 2 .. kSortTile); the direction of a tile follows the global index
+__global__ void __launch_bounds__(kSortThreads) sort_tile_kernel(unsigned long long* keys) {
+    extern __shared__ unsigned long long s[];
+    const long long base = (long long)blockIdx.x * kSortTile;
+    for (int i = threadIdx.x; i < kSortTile; i += kSortThreads) s[i] = keys[base + i];
+    for (int k = 2; k <= kSortTile; k <<= 1) tile_steps(s, base, k, k >> 1);
+    for (int i = threadIdx.x; i < kSortTile; i += kSortThreads) keys[base + i] = s[i];
+}
+
+// finish stage k inside a tile: strides kSortTile / 2 .. 1
+__global__ void __launch_bounds__(kSortThreads) sort_tile_merge_kernel(unsigned long long* keys, long long k) {
+    extern __shared__ unsigned long long s[];
+    const long long base = (long long)blockIdx.x * kSortTile;
+    for (int i = threadIdx.x; i < kSortTile; i += kSortThreads) s[i] = keys[base + i];
+    tile_steps(s, base, k, kSortTile / 2);
+    for (int i = threadIdx.x; i < kSortTile; i += kSortThreads) keys[base + i] = s[i];
+}
+
+// one stride (j >= kSortTile) of stage k across tiles
 __global__ void sort_global_step_kernel(unsigned long long* keys, long long n_pad, long long k, long long j) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_pad / 2) return;
@@ -134,21 +240,27 @@ __global__ void sort_global_step_kernel(unsigned long long* keys, long long n_pa
     if ((a < b) == desc) { keys[i] = b; keys[i + j] = a; }
 }
 
-// finish stage k inside a tile: strides kSortThreads .. 1
-__global__ void __launch_bounds__(kSortThreads) sort_tile_merge_kernel(unsigned long long* keys, long long k) {
-    __shared__ unsigned long long s[kSortTile];
-    unsigned long long* g = keys + (long long)blockIdx.x * kSortTile;
-    s[threadIdx.x] = g[threadIdx.x];
-    s[threadIdx.x + kSortThreads] = g[threadIdx.x + kSortThreads];
-    for (int j = kSortThreads; j > 0; j >>= 1) {
-        __syncthreads();
-        const int i = 2 * threadIdx.x - (threadIdx.x & (j - 1));
-        const long long gi = (long long)blockIdx.x * kSortTile + i;
-        cmp_swap_desc(s[i], s[i + j], (gi & k) == 0);
-    }
-    __syncthreads();
-    g[threadIdx.x] = s[threadIdx.x];
-    g[threadIdx.x + kSortThreads] = s[threadIdx.x + kSortThreads];
+// two strides (j and j / 2, both >= kSortTile) of stage k in one pass: every thread owns the 4 keys they connect
+__global__ void sort_global_step2_kernel(unsigned long long* keys, long long n_pad, long long k, long long j) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pad / 4) return;
+    const long long lo = j >> 1;
+    const long long i0 = ((t & ~(lo - 1)) << 2) + (t & (lo - 1));
+    unsigned long long a = keys[i0], b = keys[i0 + lo], c = keys[i0 + j], d = keys[i0 + j + lo];
+    const bool desc = (i0 & k) == 0;
+    cmp_swap_desc(a, c, desc); cmp_swap_desc(b, d, desc);
+    cmp_swap_desc(a, b, desc); cmp_swap_desc(c, d, desc);
+    keys[i0] = a; keys[i0 + lo] = b; keys[i0 + j] = c; keys[i0 + j + lo] = d;
+}
+
+cudaError_t sort_configure() {
+    static bool done = false;
+    if (done) return cudaSuccess;
+    const int bytes = kSortTile * (int)sizeof(unsigned long long);
+    cudaError_t e = cudaFuncSetAttribute(sort_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_tile_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    done = e == cudaSuccess;
+    return e;
 }
 
 }  // namespace
@@ -168,7 +280,9 @@ extern "C" int mas_region_keys_dev(const float* score, const uint8_t* in_pool, c
     return 0;
 }
 
-extern "C" size_t mas_topk_workspace_bytes(void) { return sizeof(SelectState); }
+constexpr size_t kFastStateOffset = (sizeof(SelectState) + 255) & ~(size_t)255;
+
+extern "C" size_t mas_topk_workspace_bytes(void) { return kFastStateOffset + sizeof(FastState); }
 
 extern "C" int mas_topk_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int32_t* out_count, void* workspace,
                                 size_t workspace_bytes, void* stream) {
@@ -205,22 +319,57 @@ extern "C" int mas_sort_desc_u64_dev(uint64_t* keys, int64_t n, void* stream) {
     MAS_REQUIRE(n <= (1ll << 22), MAS_E_RANGE, "sort_desc_u64: n > 2^22");
     if (n <= 1) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    MAS_CUDA_OK(sort_configure());
     long long n_pad = kSortTile;
     while (n_pad < n) n_pad <<= 1;
     unsigned long long* kk = reinterpret_cast<unsigned long long*>(keys);
+    const size_t smem = kSortTile * sizeof(unsigned long long);
     int launches = 1;
     if (n_pad > n) { sort_pad_kernel<<<(unsigned)((n_pad - n + 255) / 256), 256, 0, st>>>(kk, n, n_pad); ++launches; }
     const unsigned tiles = (unsigned)(n_pad / kSortTile);
-    sort_tile_kernel<<<tiles, kSortThreads, 0, st>>>(kk);
+    sort_tile_kernel<<<tiles, kSortThreads, smem, st>>>(kk);
     for (long long k = 2ll * kSortTile; k <= n_pad; k <<= 1) {
-        for (long long j = k >> 1; j >= kSortTile; j >>= 1) {
-            sort_global_step_kernel<<<(unsigned)((n_pad / 2 + 255) / 256), 256, 0, st>>>(kk, n_pad, k, j);
+        long long j = k >> 1;
+        while (j >= kSortTile) {
+            if ((j >> 1) >= kSortTile) {
+                sort_global_step2_kernel<<<(unsigned)((n_pad / 4 + 255) / 256), 256, 0, st>>>(kk, n_pad, k, j);
+                j >>= 2;
+            } else {
+                sort_global_step_kernel<<<(unsigned)((n_pad / 2 + 255) / 256), 256, 0, st>>>(kk, n_pad, k, j);
+                j >>= 1;
+            }
             ++launches;
         }
-        sort_tile_merge_kernel<<<tiles, kSortThreads, 0, st>>>(kk, k);
+        sort_tile_merge_kernel<<<tiles, kSortThreads, smem, st>>>(kk, k);
         ++launches;
     }
     mas::count_launches(launches);
     MAS_LAUNCH_OK("sort_desc_u64 kernels");
+    return 0;
+}
+
+extern "C" int mas_topk_sorted_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int64_t capacity,
+                                       int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    MAS_REQUIRE(keys && out && out_count && workspace, MAS_E_BADARG, "topk_sorted_u64: null pointer");
+    MAS_REQUIRE(n >= 0 && k >= 0, MAS_E_BADARG, "topk_sorted_u64: negative size");
+    MAS_REQUIRE(workspace_bytes >= mas_topk_workspace_bytes(), MAS_E_WORKSPACE, "topk_sorted_u64: workspace too small");
+    MAS_REQUIRE(capacity >= mas_sort_capacity(k) && capacity == mas_sort_capacity(capacity), MAS_E_BADARG,
+                "topk_sorted_u64: capacity must be a sort capacity >= mas_sort_capacity(k)");
+    cudaStream_t st = (cudaStream_t)stream;
+    FastState* state = reinterpret_cast<FastState*>(reinterpret_cast<char*>(workspace) + kFastStateOffset);
+    MAS_CUDA_OK(cudaMemsetAsync(state, 0, sizeof(FastState), st));
+    MAS_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)capacity * sizeof(uint64_t), st));
+    if (n > 0 && k > 0) {
+        const unsigned long long* kk = reinterpret_cast<const unsigned long long*>(keys);
+        const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, (long long)mas::sm_count() * 4);
+        fast_hist_kernel<<<blocks, 256, 0, st>>>(kk, n, state, k, 0);
+        fast_hist_kernel<<<blocks, 256, 0, st>>>(kk, n, state, k, 1);
+        fast_compact_kernel<<<blocks, 256, 0, st>>>(kk, n, state, reinterpret_cast<unsigned long long*>(out), capacity);
+        mas::count_launches(3);
+    }
+    fast_finish_kernel<<<1, 1, 0, st>>>(state, out_count, k, capacity);
+    mas::count_launches(1);
+    MAS_LAUNCH_OK("topk_sorted_u64 kernels");
+    if (n > 0 && k > 0) return mas_sort_desc_u64_dev(out, capacity, stream);
     return 0;
 }

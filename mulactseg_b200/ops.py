@@ -143,6 +143,22 @@ def sort_capacity(n: int) -> int:
     return int(_lib.load().mas_sort_capacity(int(n)))
 
 
+def topk_sorted(keys: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fast path of ``topk_keys(..., sort=True)``: bucket histogram + compaction + sort (``mas_topk_sorted_u64_dev``).
+    The device count is -1 when the candidates overflowed the buffer; the caller then uses ``topk_keys``."""
+    _want(keys, "keys", torch.int64, 1)
+    k = int(k)
+    cap = sort_capacity(max(k, 1))
+    out = torch.empty(cap, dtype=torch.int64, device=keys.device)
+    count = torch.empty(1, dtype=torch.int32, device=keys.device)
+    ws_bytes = int(_lib.load().mas_topk_workspace_bytes())
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+    with torch.cuda.device(keys.device):
+        _lib.call("mas_topk_sorted_u64_dev", keys.data_ptr(), keys.numel(), k, out.data_ptr(), cap, count.data_ptr(),
+                  ws.data_ptr(), ws_bytes, _stream(keys))
+    return out, count
+
+
 def topk_keys(keys: torch.Tensor, k: int, sort: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """The k largest non-zero keys (sorted descending if ``sort``) and a device int32 count.
 

@@ -70,11 +70,12 @@ def top_regions(scores: torch.Tensor, in_pool: torch.Tensor, image_rank_local: t
     keys = ops.region_keys(scores, in_pool, image_rank_local)
     if mdist.is_distributed(group):
         local, count = ops.topk_keys(keys, k, sort=False)
-        merged = mdist.gather_candidates(local, count, k, group)
-        best, count = ops.topk_keys(merged, k, sort=True)
-    else:
-        best, count = ops.topk_keys(keys, k, sort=True)
+        keys = mdist.gather_candidates(local, count, k, group)
+    best, count = ops.topk_sorted(keys, k)           # bucket + compaction + sort
     n = int(count.item())
+    if n < 0:                                        # candidates overflowed (heavily tied scores): exact radix select
+        best, count = ops.topk_keys(keys, k, sort=True)
+        n = int(count.item())
     return best[:n].cpu().numpy().view(np.uint64)
 
 

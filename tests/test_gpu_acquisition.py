@@ -175,6 +175,29 @@ def test_topk_and_sort_match_numpy(n, k):
     np.testing.assert_array_equal(out.cpu().numpy().view(np.uint64)[: len(want)], want)
 
 
+@pytest.mark.parametrize("n,k,ties", [(10, 3, False), (5000, 5000, False), (70001, 4097, False), (70001, 4097, True),
+                                      (300000, 100001, False), (20000, 30000, False), (300000, 1000, True)])
+def test_fast_topk_sorted_matches_numpy(n, k, ties):
+    """Bucket + compaction + sort path (mas_topk_sorted_u64_dev): identical to numpy wherever it reports success; on
+    heavily tied scores it must either succeed or report the overflow (-1) that sends the caller to the exact path."""
+    from mulactseg_b200 import ops
+    g = torch.Generator().manual_seed(n + k)
+    if ties:
+        hi = torch.randint(5, 9, (n,), generator=g, dtype=torch.int64) << 40      # 4 distinct high parts: one bucket
+    else:
+        hi = torch.randint(0, 2 ** 31 - 1, (n,), generator=g, dtype=torch.int64) << 32
+    keys = (hi | torch.randperm(n, generator=g)) * (torch.rand(n, generator=g) < 0.9)
+    got, count = ops.topk_sorted(keys.to(DEV), k)
+    cnt = int(count.item())
+    nz = np.sort(keys.numpy().astype(np.uint64)[keys.numpy() != 0])[::-1]
+    if cnt < 0:
+        assert ties and len(nz) > ops.sort_capacity(k)      # only an overflowing bucket may give up
+        got, count = ops.topk_keys(keys.to(DEV), k, sort=True)
+        cnt = int(count.item())
+    assert cnt == min(k, len(nz))
+    np.testing.assert_array_equal(got.cpu().numpy().astype(np.uint64)[:cnt], nz[:cnt])
+
+
 @pytest.mark.parametrize("method,predignore", [("my_bvsb", True), ("my_bvsb_predclsbal_pwr_banignore", True),
                                               ("my_bvsb_clsbal_v2", False)])
 def test_plugin_select_next_batch_matches_oracle(method, predignore, tmp_path):
