@@ -374,6 +374,8 @@ __global__ void __launch_bounds__(kThreads) multihot_loss_bwd_kernel(const LossP
     const bool do_choice = p.do_choice != 0, do_group = p.do_group != 0;
     const float w_one = p.coef[0] * p.inv_temp, w_multi = p.coef[1] * p.inv_temp, w_group = p.coef[3] * p.inv_temp;
     const size_t P = (size_t)p.H * p.W;
+    // rows, planes and the gradient base are 16-byte aligned: whole tiles can be zero-filled with 128-bit stores
+    const bool vec_ok = (p.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.grad) & 15) == 0);
     const long long n_tiles = tile_count(p);
     const long long warp_stride = (long long)gridDim.x * (kThreads / 32);
     for (long long tile = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += warp_stride) {
@@ -388,7 +390,26 @@ __global__ void __launch_bounds__(kThreads) multihot_loss_bwd_kernel(const LossP
         const uint32_t any_rows = __reduce_or_sync(kFullWarp, mbits);
         float* tgrad = p.grad + (size_t)t.img * C * P + off0;
         if (any_rows == 0u) {          // warp-uniform: nothing selected in the tile -> independent streaming zero stores
-            if (active) {
+            if (vec_ok) {
+                // 128-bit stores: lane -> (row l / 8 of a group of 4 rows, 4 pixels): 4 full 128-byte lines per instruction
+                const int lane = threadIdx.x & 31;
+                const int x4 = (t.x - lane) + (lane & 7) * 4;
+                if (x4 < p.W) {
+                    float* base = p.grad + (size_t)t.img * C * P + (size_t)t.y0 * p.W + x4;
+#pragma unroll
+                    for (int rg = 0; rg < kTileRows / 4; ++rg) {
+                        const int r = rg * 4 + (lane >> 3);
+                        if (r < t.rows) {
+                            float* ptr = base + (size_t)r * p.W;
+#pragma unroll
+                            for (int c = 0; c < CMAX; ++c) {
+                                if (EXACT || c < C) __stcs(reinterpret_cast<float4*>(ptr), make_float4(0.f, 0.f, 0.f, 0.f));
+                                ptr += P;
+                            }
+                        }
+                    }
+                }
+            } else if (active) {
 #pragma unroll 2
                 for (int r = 0; r < t.rows; ++r) {
                     float* ptr = tgrad + (size_t)r * p.W;

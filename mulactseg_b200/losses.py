@@ -258,21 +258,40 @@ class OnehotCEMultihotChoice(MultiChoiceCE):
 
     The reference defines multi-hot := not one-hot and asserts that this equals row-sum > 1 (:65-67), i.e. it
     raises on a selected pixel whose superpixel has no candidate class.  ``assert_partition=True`` (default)
-    keeps that check (one device sync, as in the reference); False skips it and counts such pixels in the
-    multi-hot bucket like the reference's arithmetic would."""
+    keeps that check (one device sync per call, as in the reference); ``'deferred'`` copies the counter to pinned host
+    memory asynchronously and raises at the NEXT call (or ``check_partition()``), so the host keeps running ahead of
+    the GPU; False skips it and counts such pixels in the multi-hot bucket like the reference's arithmetic would."""
     strict_multihot = False
 
     def __init__(self, num_class, temperature=1.0, reduction="mean", assert_partition=True):
         super().__init__(num_class, temperature, reduction)
         assert self.reduction == "mean"
         self.assert_partition = assert_partition
+        self._pending = None        # (pinned host copy of the empty-row count, event) of the previous call
+
+    def check_partition(self):
+        """Raise if the previous call saw a selected pixel whose superpixel has no candidate class
+        (``assert_partition='deferred'``: same assertion as the reference, without stalling the stream)."""
+        if self._pending is not None:
+            host, event = self._pending
+            self._pending = None
+            event.synchronize()
+            assert float(host[0]) == 0.0   # ..._lossdecomp.py:67
 
     def forward(self, inputs, targets, superpixels, spmasks):
+        if self.assert_partition == "deferred":
+            self.check_partition()
         out = self._losses(inputs, targets, superpixels, spmasks)
         if self.strict_multihot:
             return out[ONE_HOT], out[MULTI_STRICT]
-        if self.assert_partition:
-            assert float(out[COUNTS][2]) == 0.0   # ..._lossdecomp.py:67
+        if self.assert_partition == "deferred":
+            host = torch.empty(1, dtype=torch.float64).pin_memory() if self._pending is None else self._pending[0]
+            host.copy_(out[COUNTS][2:3], non_blocking=True)
+            event = torch.cuda.Event()
+            event.record()
+            self._pending = (host, event)
+        elif self.assert_partition:
+            assert float(out[COUNTS][2]) == 0.0   # ..._lossdecomp.py:67 (one device sync, as in the reference)
         return out[ONE_HOT], out[MULTI_NOT_ONE]
 
 
@@ -281,12 +300,13 @@ class OnehotCEMultihotChoiceVOC(OnehotCEMultihotChoice):
     strict_multihot = True
 
 
-def stage1_criterion(args, num_classes: int, voc: bool = False):
+def stage1_criterion(args, num_classes: int, voc: bool = False, assert_partition="deferred"):
     """The two criteria ``ActiveTrainer.get_criterion`` installs (``..._lossdecomp.py:78-81``), wired to share
-    one fused pass per step when ``group_ce_temp == multi_ce_temp``."""
+    one fused pass per step when ``group_ce_temp == multi_ce_temp``.  The reference's partition assertion is kept
+    but checked one step late (``assert_partition='deferred'``) so that a training step never waits for the GPU."""
     shared = SharedPass()
     group = GroupMultiLabelCE_onlymulti(args=args, num_class=num_classes, num_superpixel=args.nseg,
                                         temperature=args.group_ce_temp).share(shared)
     cls = OnehotCEMultihotChoiceVOC if voc else OnehotCEMultihotChoice
-    multi = cls(num_class=num_classes, temperature=args.multi_ce_temp).share(shared)
+    multi = cls(num_class=num_classes, temperature=args.multi_ce_temp, assert_partition=assert_partition).share(shared)
     return group, multi

@@ -18,7 +18,26 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _stream(t: torch.Tensor) -> int:
-    return torch.cuda.current_stream(t.device).cuda_stream
+    """Raw handle of torch's current stream on the tensor's device (no Stream object is built: this sits on the
+    launch path of every kernel)."""
+    return torch._C._cuda_getCurrentRawStream(t.device.index)
+
+
+class _on:
+    """``with _on(t):`` makes the tensor's device current for the C-ABI call; free when it already is."""
+    __slots__ = ("guard",)
+
+    def __init__(self, t: torch.Tensor):
+        self.guard = None if t.device.index == torch.cuda.current_device() else torch.cuda.device(t.device)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
+        return False
 
 
 def _want(t: torch.Tensor, name: str, dtype=None, dims=None):
@@ -62,7 +81,7 @@ def bvsb_segment_stats(logits: torch.Tensor, spx: torch.Tensor, nseg: int, tempe
             raise RuntimeError("prob_sum must hold B*C elements")
     if b == 0:
         return
-    with torch.cuda.device(logits.device):
+    with _on(logits):
         _lib.call("mas_bvsb_segment_stats_dev", logits.data_ptr(),
                   _lib.MAS_F32 if logits.dtype == torch.float32 else _lib.MAS_BF16, int(image_stride), spx.data_ptr(),
                   b, c, h, w, int(nseg), float(temperature), cls_sum.data_ptr(), cls_cnt.data_ptr(),
@@ -84,7 +103,7 @@ def region_scores(cls_sum: torch.Tensor, cls_cnt: torch.Tensor, class_weight: Op
     score = torch.empty(shape, dtype=torch.float32, device=cls_sum.device)
     dominant = torch.empty(shape, dtype=torch.int32, device=cls_sum.device)
     npix = torch.empty(shape, dtype=torch.int32, device=cls_sum.device) if want_npix else None
-    with torch.cuda.device(cls_sum.device):
+    with _on(cls_sum):
         _lib.call("mas_region_scores_dev", cls_sum.data_ptr(), cls_cnt.data_ptr(), _ptr(class_weight), n, c,
                   score.data_ptr(), _ptr(npix), dominant.data_ptr(), _stream(cls_sum))
     return score, npix, dominant
@@ -94,7 +113,7 @@ def minmax_nonzero(values: torch.Tensor) -> torch.Tensor:
     """Device tensor [min over non-zero entries, max over all entries]."""
     _want(values, "values", torch.float32)
     out = torch.empty(2, dtype=torch.float32, device=values.device)
-    with torch.cuda.device(values.device):
+    with _on(values):
         _lib.call("mas_minmax_nonzero_dev", values.data_ptr(), values.numel(), out.data_ptr(), _stream(values))
     return out
 
@@ -102,7 +121,7 @@ def minmax_nonzero(values: torch.Tensor) -> torch.Tensor:
 def dominant_hist(dominant: torch.Tensor, channels: int) -> torch.Tensor:
     _want(dominant, "dominant", torch.int32)
     hist = torch.zeros(channels, dtype=torch.int64, device=dominant.device)
-    with torch.cuda.device(dominant.device):
+    with _on(dominant):
         _lib.call("mas_dominant_hist_dev", dominant.data_ptr(), dominant.numel(), int(channels), hist.data_ptr(),
                   _stream(dominant))
     return hist
@@ -118,7 +137,7 @@ def finalize_scores(score: torch.Tensor, dominant: Optional[torch.Tensor], minma
         _want(minmax, "minmax", torch.float32)
     if region_weight is not None:
         _want(region_weight, "region_weight", torch.float32)
-    with torch.cuda.device(score.device):
+    with _on(score):
         _lib.call("mas_finalize_scores_dev", score.data_ptr(), _ptr(dominant), score.numel(), _ptr(minmax),
                   int(ban_class), _ptr(region_weight), _stream(score))
     return score
@@ -133,7 +152,7 @@ def region_keys(score: torch.Tensor, in_pool: torch.Tensor, image_rank: torch.Te
     if tuple(in_pool.shape) != (n, s) or image_rank.numel() != n:
         raise RuntimeError("in_pool / image_rank shape mismatch")
     keys = torch.empty(n * s, dtype=torch.int64, device=score.device)
-    with torch.cuda.device(score.device):
+    with _on(score):
         _lib.call("mas_region_keys_dev", score.data_ptr(), in_pool.data_ptr(), image_rank.data_ptr(), n, s,
                   keys.data_ptr(), _stream(score))
     return keys
@@ -153,7 +172,7 @@ def topk_sorted(keys: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]
     count = torch.empty(1, dtype=torch.int32, device=keys.device)
     ws_bytes = int(_lib.load().mas_topk_workspace_bytes())
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
-    with torch.cuda.device(keys.device):
+    with _on(keys):
         _lib.call("mas_topk_sorted_u64_dev", keys.data_ptr(), keys.numel(), k, out.data_ptr(), cap, count.data_ptr(),
                   ws.data_ptr(), ws_bytes, _stream(keys))
     return out, count
@@ -171,7 +190,7 @@ def topk_keys(keys: torch.Tensor, k: int, sort: bool = True) -> Tuple[torch.Tens
     count = torch.zeros(1, dtype=torch.int32, device=keys.device)
     ws_bytes = int(_lib.load().mas_topk_workspace_bytes())
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
-    with torch.cuda.device(keys.device):
+    with _on(keys):
         _lib.call("mas_topk_u64_dev", keys.data_ptr(), keys.numel(), k, out.data_ptr(), count.data_ptr(),
                   ws.data_ptr(), ws_bytes, _stream(keys))
         if sort and k > 1:
@@ -193,7 +212,7 @@ def multihot_info(targets: torch.Tensor, channels: int, group_mode: int) -> torc
     _want(targets, "targets", torch.uint8)
     ct = targets.shape[-1]
     info = torch.empty(targets.shape[:-1], dtype=torch.int32, device=targets.device)
-    with torch.cuda.device(targets.device):
+    with _on(targets):
         _lib.call("mas_multihot_info_dev", targets.data_ptr(), info.numel(), int(ct), int(channels), int(group_mode),
                   info.data_ptr(), _stream(targets))
     return info
@@ -221,7 +240,7 @@ def multihot_loss_forward(logits: torch.Tensor, spx: torch.Tensor, mask: torch.T
     buf = torch.zeros(8 + (n * nseg * c if want_group else 0), dtype=torch.int64, device=logits.device)
     acc = buf[:8].view(torch.float64)
     gmax = buf[8:].view(n, nseg, c) if want_group else None
-    with torch.cuda.device(logits.device):
+    with _on(logits):
         _lib.call("mas_multihot_loss_fwd_dev", logits.data_ptr(), spx.data_ptr(), _ids_dtype(spx), mask.data_ptr(),
                   info.data_ptr(), n, c, h, w, int(nseg), float(temperature), int(flags), acc.data_ptr(), _ptr(gmax),
                   _stream(logits))
@@ -237,7 +256,7 @@ def multihot_loss_backward(logits: torch.Tensor, spx: torch.Tensor, mask: torch.
     if coef.numel() != 4:
         raise RuntimeError("coef must hold 4 floats")
     grad = torch.empty_like(logits)
-    with torch.cuda.device(logits.device):
+    with _on(logits):
         _lib.call("mas_multihot_loss_bwd_dev", logits.data_ptr(), spx.data_ptr(), _ids_dtype(spx), mask.data_ptr(),
                   info.data_ptr(), _ptr(gmax), coef.data_ptr(), n, c, h, w, int(nseg), float(temperature), int(flags),
                   grad.data_ptr(), _stream(logits))
@@ -248,7 +267,7 @@ def multihot_loss_finish(acc: torch.Tensor) -> torch.Tensor:
     """(8,) f64 bucket sums / counts -> (6,) f32 normalised losses (see ``mas_multihot_loss_finish_dev``)."""
     _want(acc, "acc", torch.float64, 1)
     losses = torch.empty(6, dtype=torch.float32, device=acc.device)
-    with torch.cuda.device(acc.device):
+    with _on(acc):
         _lib.call("mas_multihot_loss_finish_dev", acc.data_ptr(), losses.data_ptr(), _stream(acc))
     return losses
 
@@ -260,7 +279,7 @@ def multihot_loss_coef(acc: torch.Tensor, grad_losses: torch.Tensor) -> torch.Te
     if grad_losses.numel() != 6:
         raise RuntimeError("grad_losses must hold 6 floats")
     coef = torch.empty(4, dtype=torch.float32, device=acc.device)
-    with torch.cuda.device(acc.device):
+    with _on(acc):
         _lib.call("mas_multihot_loss_coef_dev", acc.data_ptr(), grad_losses.data_ptr(), coef.data_ptr(), _stream(acc))
     return coef
 
@@ -270,7 +289,7 @@ def candidate_argmax(logits: torch.Tensor, spx: torch.Tensor, mask: torch.Tensor
     """(N,H,W) uint8 labels: arg-max of logit * multi-hot row on selected pixels, 255 elsewhere."""
     n, c, h, w = _loss_args(logits, spx, mask, info, nseg)
     labels = torch.empty((n, h, w), dtype=torch.uint8, device=logits.device)
-    with torch.cuda.device(logits.device):
+    with _on(logits):
         _lib.call("mas_candidate_argmax_dev", logits.data_ptr(), spx.data_ptr(), _ids_dtype(spx), mask.data_ptr(),
                   info.data_ptr(), n, c, h, w, int(nseg), labels.data_ptr(), _stream(logits))
     return labels
@@ -308,7 +327,7 @@ def proto_labeller(feats: torch.Tensor, logits: torch.Tensor, targets: torch.Ten
     labels = torch.empty((h, w), dtype=torch.uint8, device=feats.device)
     status = torch.zeros(1, dtype=torch.int32, device=feats.device)
     ws = _labeller_workspace(feats.device, fch, c, h, w, nseg)
-    with torch.cuda.device(feats.device):
+    with _on(feats):
         _lib.call("mas_proto_labeller_dev", feats.data_ptr(), fch, logits.data_ptr(), c, targets.data_ptr(), ct,
                   mask.data_ptr(), spx.data_ptr(), _ids_dtype(spx), h, w, nseg, int(bool(only_multihot)),
                   _lib.MAS_THRESHOLD_MEDIAN if threshold == "median" else _lib.MAS_THRESHOLD_MIN,
@@ -331,7 +350,7 @@ def multihot_labels(spx: torch.Tensor, target: torch.Tensor, keep: torch.Tensor,
     size = torch.empty((nseg,), dtype=torch.int32, device=spx.device)
     need = int(_lib.load().mas_multihot_labels_workspace_bytes(int(nseg), int(num_classes)))
     ws = torch.empty(need, dtype=torch.uint8, device=spx.device)
-    with torch.cuda.device(spx.device):
+    with _on(spx):
         _lib.call("mas_multihot_labels_dev", spx.data_ptr(), _ids_dtype(spx), target.data_ptr(), keep.data_ptr(), h, w,
                   int(nseg), int(num_classes), int(trim_kernel_size), multi_hot.data_ptr(), size.data_ptr(), ws.data_ptr(),
                   need, _stream(spx))

@@ -195,6 +195,14 @@ def test_empty_candidate_row_raises_like_the_reference():
         L.OnehotCEMultihotChoice(c, temperature=1.0)(x, trg, spx, mask)
     one, multi = L.OnehotCEMultihotChoice(c, temperature=1.0, assert_partition=False)(x, trg, spx, mask)
     assert torch.isfinite(one) and torch.isfinite(multi)
+    # deferred check (what stage1_criterion installs): same assertion, raised by the NEXT call instead of stalling this one
+    lazy = L.OnehotCEMultihotChoice(c, temperature=1.0, assert_partition="deferred")
+    lazy(x, trg, spx, mask)
+    with pytest.raises(AssertionError):
+        lazy(x, trg, spx, mask)
+    lazy(x, trg, spx, mask)
+    with pytest.raises(AssertionError):
+        lazy.check_partition()
     with pytest.raises(RuntimeError):
         L.MultiChoiceCE_(c)(x.cpu(), trg.cpu(), spx.cpu(), mask.cpu())      # no CPU path
 

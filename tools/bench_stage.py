@@ -61,6 +61,18 @@ def bench_losses(res, profile, only_rho=None, only_exact=None):
         def step():
             fwd().backward()
 
+        if os.environ.get("MAS_PYPROF"):      # where does the host time of a step go?
+            import cProfile, pstats
+            for _ in range(20):
+                step()
+            torch.cuda.synchronize()
+            pr = cProfile.Profile()
+            pr.enable()
+            for _ in range(200):
+                step()
+            torch.cuda.synchronize()
+            pr.disable()
+            pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
         with torch.no_grad():
             ms_f = time_ms(lambda: fwd(), iters=3 if profile else 10)
         ms_fb = time_ms(step, iters=3 if profile else 10)
