@@ -222,6 +222,7 @@ constexpr int kFeatBatch = 16;
 constexpr int kSlices = 4;         // CTAs that share the pixels of one superpixel
 
 // sproto layout: [channel][kGroup] so that the kGroup operands of one channel are two 128-bit broadcast reads
+// (a 4-prototype instantiation for sparse batches was measured slower: the compiler keeps fewer loads in flight)
 __device__ __forceinline__ void dot_all(const LabelParams& p, const float* __restrict__ sproto, int pix, float (&acc)[kGroup]) {
 #pragma unroll
     for (int g = 0; g < kGroup; ++g) acc[g] = 0.f;
@@ -394,14 +395,30 @@ __global__ void __launch_bounds__(kAssignThreads) proto_threshold_kernel(LabelPa
                     const unsigned int n = hist[0];
                     empty = n == 0u;
                     if (threadIdx.x == 0) sel_rank = n ? (n - 1u) / 2u : 0u;
-                } else if (threadIdx.x == 0) {
-                    unsigned int rank = sel_rank, bin = 0u;
-                    for (; bin < 255u; ++bin) {
-                        if (rank < hist[bin]) break;
-                        rank -= hist[bin];
+                } else if (threadIdx.x < 32) {
+                    // warp 0: first bin whose cumulative count exceeds the rank (lane l owns bins 8 l .. 8 l + 7)
+                    const int lane = threadIdx.x;
+                    unsigned int h[8], mine = 0u;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { h[i] = hist[lane * 8 + i]; mine += h[i]; }
+                    unsigned int incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned int y = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += y;
                     }
-                    sel_rank = rank;
-                    sel_prefix = prefix | (bin << shift);
+                    const unsigned int rank = sel_rank;
+                    const unsigned int owners = __ballot_sync(0xffffffffu, rank < incl);
+                    const int owner = owners ? __ffs(owners) - 1 : 31;
+                    if (lane == owner) {
+                        unsigned int r = rank - (incl - mine), bin = 0u;
+#pragma unroll
+                        for (int i = 0; i < 7; ++i) {
+                            if (bin == (unsigned)i && r >= h[i]) { r -= h[i]; bin = i + 1; }
+                        }
+                        sel_rank = r;
+                        sel_prefix = prefix | (((unsigned)lane * 8u + bin) << shift);
+                    }
                 }
                 __syncthreads();
                 if (empty) break;
