@@ -19,6 +19,8 @@
 // the superpixel changes.  Backward recomputes the softmax and writes the dense gradient once.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 namespace {
@@ -37,6 +39,7 @@ struct LossParams {
     float inv_temp;  // 1 / T
     float scale;     // log2(e) / T
     int do_choice, do_group;
+    int tile_rows;                // rows per tile (<= kTileRows)
     double* acc;                  // fwd: [0..5] one-hot / multi-hot / empty {sum, count}
     unsigned long long* gmax;     // (n_img * S * C) packed maxima
     const float* coef;            // bwd: {w_onehot, w_multihot, w_empty, w_group} = d total / d bucket sum
@@ -68,7 +71,7 @@ __global__ void multihot_info_kernel(const uint8_t* __restrict__ targets, long l
 //      selected pixel ends there (forward) or is zero-filled with independent streaming stores (backward);
 //   2. rows are software-pipelined three deep: while row r is computed, the C' logits and the candidate word of row
 //      r + 1 and the id of row r + 2 are in flight (loads of unselected pixels are predicated off).
-constexpr int kTileRows = 16;
+constexpr int kTileRows = 16;          // most rows a tile can have (the launcher picks 4, 8 or 16: see launch_one)
 constexpr uint32_t kFullWarp = 0xffffffffu;
 
 __device__ __forceinline__ int clamp_id(long long v) { return (v < 0 || v > 0x7fffffffLL) ? -1 : (int)v; }
@@ -119,19 +122,19 @@ struct Tile {
 };
 
 __device__ __forceinline__ long long tile_count(const LossParams& p) {
-    return (long long)p.n_img * ((p.W + 31) / 32) * ((p.H + kTileRows - 1) / kTileRows);
+    return (long long)p.n_img * ((p.W + 31) / 32) * ((p.H + p.tile_rows - 1) / p.tile_rows);
 }
 
 __device__ __forceinline__ Tile make_tile(const LossParams& p, long long tile) {
     Tile t;
-    const int tiles_x = (p.W + 31) / 32, tiles_y = (p.H + kTileRows - 1) / kTileRows;
+    const int tiles_x = (p.W + 31) / 32, tiles_y = (p.H + p.tile_rows - 1) / p.tile_rows;
     const long long per_img = (long long)tiles_x * tiles_y;
     t.img = (int)(tile / per_img);
     const int rem = (int)(tile - (long long)t.img * per_img);
     const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
     t.x = tx * 32 + (threadIdx.x & 31);
-    t.y0 = ty * kTileRows;
-    t.rows = min(p.H - t.y0, kTileRows);
+    t.y0 = ty * p.tile_rows;
+    t.rows = min(p.H - t.y0, p.tile_rows);
     return t;
 }
 
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(kThreads) multihot_loss_fwd_kernel(const LossP
         int cur = -1;
         long long cur_base = 0;   // table offset of superpixel `cur`
 #pragma unroll 1
-        for (int r = 0; r < kTileRows; ++r) {
+        for (int r = 0; r < t.rows; ++r) {
             float v[CMAX];
             int id;
             uint32_t inf;
@@ -396,8 +399,8 @@ __global__ void __launch_bounds__(kThreads) multihot_loss_bwd_kernel(const LossP
                 const int x4 = (t.x - lane) + (lane & 7) * 4;
                 if (x4 < p.W) {
                     float* base = p.grad + (size_t)t.img * C * P + (size_t)t.y0 * p.W + x4;
-#pragma unroll
-                    for (int rg = 0; rg < kTileRows / 4; ++rg) {
+#pragma unroll 1
+                    for (int rg = 0; rg * 4 < t.rows; ++rg) {
                         const int r = rg * 4 + (lane >> 3);
                         if (r < t.rows) {
                             float* ptr = base + (size_t)r * p.W;
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(kThreads) multihot_loss_bwd_kernel(const LossP
         RowPipe<CMAX, EXACT, IdT> pipe(p);
         pipe.start(t, C, P, off0, mbits);
 #pragma unroll 1
-        for (int r = 0; r < kTileRows; ++r) {
+        for (int r = 0; r < t.rows; ++r) {
             float v[CMAX];
             int id;
             uint32_t inf;
@@ -434,7 +437,7 @@ __global__ void __launch_bounds__(kThreads) multihot_loss_bwd_kernel(const LossP
             const bool group = do_group && (inf & kGroupBit) && bits != 0u;
             const bool live = id >= 0 && (group || (do_choice && bits != 0u));     // does any gradient reach this pixel?
             const bool any_live = __any_sync(kFullWarp, live);
-            if (!active || r >= t.rows) continue;
+            if (!active) continue;
             float* gbase = tgrad + (size_t)r * p.W;
             if (!any_live) {
                 float* ptr = gbase;
@@ -530,10 +533,14 @@ int resident_ctas(K kernel, size_t smem) {
     return n;
 }
 
+int env_tile_rows() {
+    const char* v = getenv("MAS_LOSS_TILE_ROWS");       // development switch
+    const int r = (v && *v) ? atoi(v) : 0;
+    return (r == 4 || r == 8 || r == 16) ? r : 0;
+}
+
 template <int CMAX, bool EXACT, typename IdT>
-cudaError_t launch_one(const LossParams& p, bool backward, bool accurate, cudaStream_t stream) {
-    const long long tiles = (long long)p.n_img * ((p.W + 31) / 32) * ((p.H + kTileRows - 1) / kTileRows);
-    const long long want = (tiles + kThreads / 32 - 1) / (kThreads / 32);
+cudaError_t launch_one(LossParams p, bool backward, bool accurate, cudaStream_t stream) {
     // forward: running maxima (u64) + softmax numerators (f32) per (class, thread); backward: the numerators
     const size_t smem = (size_t)p.C * kThreads * (backward ? sizeof(float) : sizeof(unsigned long long) + sizeof(float));
     // persistent grid: one wave of resident CTAs (per instantiation; the generic channel padding changes smem by < 2x)
@@ -545,6 +552,17 @@ cudaError_t launch_one(const LossParams& p, bool backward, bool accurate, cudaSt
         else if (accurate) per_sm[which] = resident_ctas(multihot_loss_fwd_kernel<CMAX, EXACT, IdT, true>, smem_max);
         else per_sm[which] = resident_ctas(multihot_loss_fwd_kernel<CMAX, EXACT, IdT, false>, smem_max);
     }
+    // Tile height: the cost of a tile is the number of its rows that hold selected pixels, served one after the other by
+    // ONE warp, so short tiles spread the selected superpixels over more warps (what matters when few pixels are
+    // labelled); tall tiles flush the private maxima less often.  Aim at >= 8 tiles per resident warp.
+    const long long warps = (long long)mas::sm_count() * per_sm[which] * (kThreads / 32);
+    const long long strips = (long long)p.n_img * ((p.W + 31) / 32);
+    int rows = kTileRows;
+    while (rows > 4 && strips * ((p.H + rows - 1) / rows) < 8 * warps) rows >>= 1;
+    if (env_tile_rows()) rows = env_tile_rows();
+    p.tile_rows = rows;
+    const long long tiles = strips * ((p.H + rows - 1) / rows);
+    const long long want = (tiles + kThreads / 32 - 1) / (kThreads / 32);
     const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)mas::sm_count() * per_sm[which]));
     if (backward) {
         multihot_loss_bwd_kernel<CMAX, EXACT, IdT><<<blocks, kThreads, smem, stream>>>(p);
