@@ -243,7 +243,7 @@ def run_ours(args):
             stats.join()
             e1.record()
             ev_pairs.append((e0, e1))
-        scores, _ = acq.finalize(stats, spec, COEFF, REF_BATCH, None)
+        scores, _ = acq.finalize(stats, spec, COEFF, REF_BATCH, None, [n_loc] * world)
         keys = selection.top_regions(scores, in_pool, image_rank, k_sel, None)   # host uint64, sorted descending
         tie = (keys & np.uint64(0xFFFFFFFF)).astype(np.int64)                    # == global region index here
         return selection.cumulative_cut(cost_all[tie], BUDGET)

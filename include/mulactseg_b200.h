@@ -149,6 +149,14 @@ int mas_sort_desc_u64_dev(uint64_t* keys, int64_t n, void* stream);
 int mas_topk_sorted_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int64_t capacity, int32_t* out_count,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* mas_topk_candidates_u64_dev -- the first half of mas_topk_sorted_u64_dev (histograms + compaction, no sort): a SUPERSET of
+ * the k largest keys, unordered, in out[0 .. count); remaining slots are 0 ("no key").  *out_count = count (>= min(k,
+ * #non-zero keys), <= capacity) or -1 on overflow.  Used per GPU before the all-gather of the multi-GPU merge: the merged
+ * candidates go through mas_topk_sorted_u64_dev once.
+ */
+int mas_topk_candidates_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int64_t capacity,
+                                int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ host-buffer entries (end-to-end)
  *
  * mas_acquisition_host -- the whole scoring pass of one selector with HOST buffers.  Streams

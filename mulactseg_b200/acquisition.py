@@ -135,18 +135,19 @@ def predicted_class_weights(prob_sum_all: torch.Tensor, pixels_per_image: int, r
     return (float(coeff) * pbar + 1.0) ** (-2)
 
 
-def finalize(stats: RegionStats, spec: SelectorSpec, coeff: float = 0.0, ref_batch: int = 1, group=None):
+def finalize(stats: RegionStats, spec: SelectorSpec, coeff: float = 0.0, ref_batch: int = 1, group=None, shard_counts=None):
     """Selector epilogue -> (scores (n,S) f32, dominant (n,S) i32) on the device.
 
     With a process group the pool-wide quantities (class means, min/max, dominant-class histogram) are
-    exchanged over it; each rank keeps the scores of its own shard.
+    exchanged over it; each rank keeps the scores of its own shard.  ``shard_counts`` = images per rank when known
+    (``dist.shard_sizes``): the gather of the class-probability sums then needs no size exchange / host sync.
     """
     stats.join()
     weight = None
     if spec.weighting == "predclsbal":
         if stats.prob_sum is None:
             raise RuntimeError("predclsbal weighting needs RegionStats(need_prob=True)")
-        prob_all = mdist.all_gather_rows(stats.prob_sum, group)
+        prob_all = mdist.all_gather_rows(stats.prob_sum, group, shard_counts)
         weight = predicted_class_weights(prob_all, stats.pixels_per_image, ref_batch, coeff).contiguous()
     score, _, dominant = ops.region_scores(stats.cls_sum, stats.cls_cnt, weight)
     minmax = None

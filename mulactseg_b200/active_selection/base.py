@@ -93,7 +93,7 @@ class RegionSelector(object):
         if stats is None:
             raise RuntimeError("empty pool shard: fewer pool images than ranks")
         scores, dominant = acquisition.finalize(stats, self.spec, getattr(self.args, "cls_weight_coeff", 0.0),
-                                                self.batch_size, self.group)
+                                                self.batch_size, self.group, mdist.shard_sizes(n_total, world))
         return PoolScores(scores, dominant, lo, hi, n_total, self.num_superpixels)
 
     # ------------------------------------------------------------------ reference-compatible entry points

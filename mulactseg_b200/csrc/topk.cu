@@ -182,9 +182,9 @@ __global__ void __launch_bounds__(256) fast_compact_kernel(const unsigned long l
     }
 }
 
-__global__ void fast_finish_kernel(const FastState* st, int32_t* out_count, long long k, long long capacity) {
+__global__ void fast_finish_kernel(const FastState* st, int32_t* out_count, long long k, long long capacity, int clamp) {
     const long long c = st->count;
-    *out_count = c > capacity ? -1 : (int32_t)min(c, k);
+    *out_count = c > capacity ? -1 : (int32_t)(clamp ? min(c, k) : c);
 }
 
 // ---------------------------------------------------------------------------------------- bitonic sort (descending)
@@ -348,13 +348,16 @@ extern "C" int mas_sort_desc_u64_dev(uint64_t* keys, int64_t n, void* stream) {
     return 0;
 }
 
-extern "C" int mas_topk_sorted_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int64_t capacity,
-                                       int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
-    MAS_REQUIRE(keys && out && out_count && workspace, MAS_E_BADARG, "topk_sorted_u64: null pointer");
-    MAS_REQUIRE(n >= 0 && k >= 0, MAS_E_BADARG, "topk_sorted_u64: negative size");
-    MAS_REQUIRE(workspace_bytes >= mas_topk_workspace_bytes(), MAS_E_WORKSPACE, "topk_sorted_u64: workspace too small");
+namespace {
+
+// histograms + compaction: out[0 .. count) holds every key from the 24-bit prefix of the k-th largest key upwards
+int fast_candidates(const char* what, const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int64_t capacity, int32_t* out_count,
+                    void* workspace, size_t workspace_bytes, void* stream, bool clamp_count) {
+    MAS_REQUIRE(keys && out && out_count && workspace, MAS_E_BADARG, "%s: null pointer", what);
+    MAS_REQUIRE(n >= 0 && k >= 0, MAS_E_BADARG, "%s: negative size", what);
+    MAS_REQUIRE(workspace_bytes >= mas_topk_workspace_bytes(), MAS_E_WORKSPACE, "%s: workspace too small", what);
     MAS_REQUIRE(capacity >= mas_sort_capacity(k) && capacity == mas_sort_capacity(capacity), MAS_E_BADARG,
-                "topk_sorted_u64: capacity must be a sort capacity >= mas_sort_capacity(k)");
+                "%s: capacity must be a sort capacity >= mas_sort_capacity(k)", what);
     cudaStream_t st = (cudaStream_t)stream;
     FastState* state = reinterpret_cast<FastState*>(reinterpret_cast<char*>(workspace) + kFastStateOffset);
     MAS_CUDA_OK(cudaMemsetAsync(state, 0, sizeof(FastState), st));
@@ -367,9 +370,23 @@ extern "C" int mas_topk_sorted_u64_dev(const uint64_t* keys, int64_t n, int64_t 
         fast_compact_kernel<<<blocks, 256, 0, st>>>(kk, n, state, reinterpret_cast<unsigned long long*>(out), capacity);
         mas::count_launches(3);
     }
-    fast_finish_kernel<<<1, 1, 0, st>>>(state, out_count, k, capacity);
+    fast_finish_kernel<<<1, 1, 0, st>>>(state, out_count, k, capacity, clamp_count ? 1 : 0);
     mas::count_launches(1);
-    MAS_LAUNCH_OK("topk_sorted_u64 kernels");
+    MAS_LAUNCH_OK(what);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int mas_topk_candidates_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int64_t capacity,
+                                           int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    return fast_candidates("topk_candidates_u64", keys, n, k, out, capacity, out_count, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int mas_topk_sorted_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int64_t capacity,
+                                       int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    const int rc = fast_candidates("topk_sorted_u64", keys, n, k, out, capacity, out_count, workspace, workspace_bytes, stream, true);
+    if (rc != 0) return rc;
     if (n > 0 && k > 0) return mas_sort_desc_u64_dev(out, capacity, stream);
     return 0;
 }

@@ -38,15 +38,19 @@ def shard_sizes(n_items: int, world: int) -> List[int]:
     return [shard_range(n_items, r, world)[1] - shard_range(n_items, r, world)[0] for r in range(world)]
 
 
-def all_gather_rows(local: torch.Tensor, group=None) -> torch.Tensor:
-    """Concatenate per-rank (n_r, ...) tensors along dim 0 in rank order (n_r may differ by rank)."""
+def all_gather_rows(local: torch.Tensor, group=None, counts: Optional[List[int]] = None) -> torch.Tensor:
+    """Concatenate per-rank (n_r, ...) tensors along dim 0 in rank order (n_r may differ by rank).
+    ``counts`` = the n_r of every rank when the caller knows them (``shard_sizes``): saves a collective and a host sync."""
     if not is_distributed(group):
         return local
     world = td.get_world_size(group)
-    counts = torch.zeros(world, dtype=torch.int64, device=local.device)
-    counts[td.get_rank(group)] = local.shape[0]
-    td.all_reduce(counts, op=td.ReduceOp.SUM, group=group)
-    counts = counts.tolist()
+    if counts is None:
+        seen = torch.zeros(world, dtype=torch.int64, device=local.device)
+        seen[td.get_rank(group)] = local.shape[0]
+        td.all_reduce(seen, op=td.ReduceOp.SUM, group=group)
+        counts = seen.tolist()
+    elif len(counts) != world or counts[td.get_rank(group)] != local.shape[0]:
+        raise RuntimeError(f"all_gather_rows: counts {counts} do not match this rank's {local.shape[0]} rows")
     width = max(counts)
     padded = local.new_zeros((width,) + tuple(local.shape[1:]))
     padded[: local.shape[0]] = local
@@ -65,6 +69,12 @@ def all_reduce_minmax(minmax: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat([lo, hi]).contiguous()
 
 
+def all_reduce_min(t: torch.Tensor, group=None) -> torch.Tensor:
+    if is_distributed(group):
+        td.all_reduce(t, op=td.ReduceOp.MIN, group=group)
+    return t
+
+
 def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
     if is_distributed(group):
         td.all_reduce(t, op=td.ReduceOp.SUM, group=group)
@@ -74,7 +84,7 @@ def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
 def gather_candidates(keys: torch.Tensor, count: torch.Tensor, k: int, group=None) -> torch.Tensor:
     """All ranks' candidate keys -> one flat int64 tensor on every rank (unused slots are 0 = 'no key').
 
-    ``keys`` holds this rank's k best keys in its first ``count`` slots (anything after is ignored).
+    ``keys`` holds this rank's candidates in its first ``count`` slots, ``count`` <= k (anything after is ignored).
     """
     local = keys[:k].clone()
     slot = torch.arange(k, device=keys.device)

@@ -162,9 +162,11 @@ def sort_capacity(n: int) -> int:
     return int(_lib.load().mas_sort_capacity(int(n)))
 
 
-def topk_sorted(keys: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Fast path of ``topk_keys(..., sort=True)``: bucket histogram + compaction + sort (``mas_topk_sorted_u64_dev``).
-    The device count is -1 when the candidates overflowed the buffer; the caller then uses ``topk_keys``."""
+def topk_sorted(keys: torch.Tensor, k: int, sort: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fast path of ``topk_keys``: bucket histograms + compaction (+ sort) -- ``mas_topk_sorted_u64_dev`` /
+    ``mas_topk_candidates_u64_dev``.  ``sort=True``: the k largest keys, descending, count = min(k, #keys);
+    ``sort=False``: an unordered superset of them, count = its size.  The device count is -1 when the candidates
+    overflowed the buffer (``sort_capacity(k)`` slots); the caller then uses ``topk_keys``."""
     _want(keys, "keys", torch.int64, 1)
     k = int(k)
     cap = sort_capacity(max(k, 1))
@@ -173,8 +175,8 @@ def topk_sorted(keys: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]
     ws_bytes = int(_lib.load().mas_topk_workspace_bytes())
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
     with _on(keys):
-        _lib.call("mas_topk_sorted_u64_dev", keys.data_ptr(), keys.numel(), k, out.data_ptr(), cap, count.data_ptr(),
-                  ws.data_ptr(), ws_bytes, _stream(keys))
+        _lib.call("mas_topk_sorted_u64_dev" if sort else "mas_topk_candidates_u64_dev", keys.data_ptr(), keys.numel(), k,
+                  out.data_ptr(), cap, count.data_ptr(), ws.data_ptr(), ws_bytes, _stream(keys))
     return out, count
 
 

@@ -65,15 +65,25 @@ def top_regions(scores: torch.Tensor, in_pool: torch.Tensor, image_rank_local: t
     """Sorted (descending) keys of the k best pool regions over ALL ranks, as a host uint64 array.
 
     scores / in_pool: this rank's (n_local, S) shard; image_rank_local: global ranks of its images.
-    Per rank: key -> radix-select k -> all_gather (k x 8 B per rank) -> select + sort k on every rank.
+    Per rank: key -> candidate superset of its k best (<= sort_capacity(k) slots) -> all_gather -> select + sort k on
+    every rank; no host sync before the final count.
     """
-    keys = ops.region_keys(scores, in_pool, image_rank_local)
-    if mdist.is_distributed(group):
-        local, count = ops.topk_keys(keys, k, sort=False)
-        keys = mdist.gather_candidates(local, count, k, group)
-    best, count = ops.topk_sorted(keys, k)           # bucket + compaction + sort
+    local_keys = ops.region_keys(scores, in_pool, image_rank_local)
+    distributed = mdist.is_distributed(group)
+    keys, worst = local_keys, None
+    if distributed:
+        # per GPU: an unordered superset of its k best keys (two histograms + compaction, no sort)
+        local, count = ops.topk_sorted(local_keys, k, sort=False)
+        worst = mdist.all_reduce_min(count.to(torch.int64), group)       # -1 if the buffer overflowed on any rank
+        keys = mdist.gather_candidates(local, count, local.numel(), group)
+    best, count = ops.topk_sorted(keys, k)           # two bucket histograms + compaction + sort
     n = int(count.item())
-    if n < 0:                                        # candidates overflowed (heavily tied scores): exact radix select
+    if n < 0 or (worst is not None and int(worst.item()) < 0):
+        # massively tied scores overflowed a candidate buffer somewhere: every rank redoes the exact radix select
+        keys = local_keys
+        if distributed:
+            local, count = ops.topk_keys(local_keys, k, sort=False)
+            keys = mdist.gather_candidates(local, count, k, group)
         best, count = ops.topk_keys(keys, k, sort=True)
         n = int(count.item())
     return best[:n].cpu().numpy().view(np.uint64)

@@ -34,6 +34,10 @@ def _worker(rank, world, port, n_img, nseg, c, k, out_dir):
 
         # (1) class weights from gathered per-image sums == single process (mean of per-batch means, batches of 4)
         gathered = mdist.all_gather_rows(prob_sum[lo:hi].contiguous())
+        known = mdist.all_gather_rows(prob_sum[lo:hi].contiguous(), None, mdist.shard_sizes(n_img, world))
+        assert torch.equal(gathered, known)                      # known shard sizes: same rows, no size exchange
+        worst = mdist.all_reduce_min(torch.tensor([5 - 6 * rank], dtype=torch.int64))
+        assert int(worst) == 5 - 6 * (world - 1)
         w_dist = acq.predicted_class_weights(gathered, 1000, 4, 6.0)
         w_one = acq.predicted_class_weights(prob_sum, 1000, 4, 6.0)
         assert torch.equal(w_dist, w_one)
