@@ -46,6 +46,7 @@ extern "C" {
 /* element type of superpixel id maps (the reference hands int64 maps over: ext_transforms.py:389,406) */
 #define MAS_I32 0
 #define MAS_I64 1
+#define MAS_U8 2      /* label maps only (mas_miou_counts_dev) */
 
 int mas_abi_version(void);
 const char* mas_last_error(void);
@@ -305,6 +306,29 @@ size_t mas_multihot_labels_workspace_bytes(int nseg, int num_classes);
 int mas_multihot_labels_dev(const void* ids, int ids_dtype, const uint8_t* target, const uint8_t* keep,
                             int height, int width, int nseg, int num_classes, int trim_kernel_size,
                             uint8_t* multi_hot, int32_t* size, void* workspace, size_t workspace_bytes, void* stream);
+
+/* mas_dominant_labels_dev -- ONE image of RegionCityscapesDominantAll.__getitem__ (dataloader/region_dataset.py:201-240;
+ * tools/label_assignment_dominant.py): inside every superpixel listed in the region dict (keep == 1) the pixels that are
+ * not 'ignore' take the most frequent train id among them (the smallest id on a tie: np.unique order + argmax); label 255
+ * and the pixels of other superpixels are copied.  ids (H, W) int32|int64, target / out (H, W) uint8.
+ */
+size_t mas_dominant_labels_workspace_bytes(int nseg, int num_classes);
+int mas_dominant_labels_dev(const void* ids, int ids_dtype, const uint8_t* target, const uint8_t* keep, int height, int width,
+                            int nseg, int num_classes, uint8_t* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ evaluation counters
+ *
+ * mas_miou_counts_dev -- utils/miou.py:23-54 (MeanIoU._after_step / _after_step_within_predregion) in one pass:
+ *   a pixel is kept when target != ignore_label (MAS_MIOU_BY_TARGET) or output != ignore_label (MAS_MIOU_BY_OUTPUT);
+ *   counts[c] += kept pixels with target == c                          (total_seen)
+ *   counts[num_classes + c]   += ... with target == c == output        (total_correct)
+ *   counts[2*num_classes + c] += kept pixels with output == c          (total_positive)
+ * outputs / targets: n labels of the same dtype (MAS_I64 | MAS_I32 | MAS_U8); counts: 3 * num_classes uint64, ACCUMULATED.
+ */
+#define MAS_MIOU_BY_TARGET 0
+#define MAS_MIOU_BY_OUTPUT 1
+int mas_miou_counts_dev(const void* outputs, const void* targets, int labels_dtype, int64_t n, int num_classes,
+                        int64_t ignore_label, int mode, uint64_t* counts, void* stream);
 
 #ifdef __cplusplus
 }

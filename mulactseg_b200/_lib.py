@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmulactseg_b200.so")
 
 MAS_F32, MAS_BF16 = 0, 1
-MAS_I32, MAS_I64 = 0, 1
+MAS_I32, MAS_I64, MAS_U8 = 0, 1, 2
+MAS_MIOU_BY_TARGET, MAS_MIOU_BY_OUTPUT = 0, 1
 MAS_GROUP_ALL, MAS_GROUP_ONLYMULTI = 0, 1
 MAS_LOSS_CHOICE, MAS_LOSS_GROUP, MAS_LOSS_EXACT_SOFTMAX = 1, 2, 4
 MAS_MAX_LOSS_CLASSES = 31
@@ -55,6 +56,10 @@ SIGNATURES = {
     "mas_multihot_labels_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mas_multihot_labels_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                         c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mas_dominant_labels_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "mas_dominant_labels_dev": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                        c_size_t, c_void_p]),
+    "mas_miou_counts_dev": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_int, c_void_p, c_void_p]),
     "mas_multihot_loss_bwd_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                           c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
 }

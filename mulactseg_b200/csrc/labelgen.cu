@@ -86,6 +86,39 @@ __global__ void label_rows_kernel(const int32_t* __restrict__ hist, const uint8_
     size[s] = n;
 }
 
+// ---------------------------------------------------------------------------------------- dominant label assignment
+// dataloader/region_dataset.py:201-240 (RegionCityscapesDominantAll.__getitem__; tools/label_assignment_dominant.py):
+//   for p in preserving_labels:  mask = (superpixel == p) & (target != 255);  u, c = np.unique(target[mask]);
+//       target[mask] = u[c.argmax()]            -- the smallest class wins a tie (np.unique sorts, argmax takes the first)
+// i.e. the untrimmed histogram above, an arg-max per superpixel and one relabelling pass.
+__global__ void dominant_pick_kernel(const int32_t* __restrict__ hist, const uint8_t* __restrict__ keep, int S, int C,
+                                     uint8_t* __restrict__ dom) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    int best = 0, arg = 255;
+    if (keep[s]) {
+        const int32_t* h = hist + (size_t)s * (C + 1);
+        for (int c = 0; c < C; ++c) {
+            if (h[c] > best) { best = h[c]; arg = c; }
+        }
+    }
+    dom[s] = (uint8_t)arg;
+}
+
+template <typename IdT>
+__global__ void dominant_relabel_kernel(const void* __restrict__ ids, const uint8_t* __restrict__ target, long long P, int S, int C,
+                                        const uint8_t* __restrict__ dom, uint8_t* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+        const uint8_t t = target[i];
+        uint8_t o = t;
+        if (t < C) {                                  // ignore (255) and anything that is not a train id stay as they are
+            const long long s = raw_id<IdT>(ids, (size_t)i);
+            if (s >= 0 && s < S && dom[s] != 255) o = dom[s];
+        }
+        out[i] = o;
+    }
+}
+
 }  // namespace
 
 extern "C" size_t mas_multihot_labels_workspace_bytes(int nseg, int num_classes) {
@@ -115,5 +148,39 @@ extern "C" int mas_multihot_labels_dev(const void* ids, int ids_dtype, const uin
     label_rows_kernel<<<(nseg + threads - 1) / threads, threads, 0, st>>>(hist, keep, nseg, num_classes, trim_kernel_size, multi_hot, size);
     mas::count_launches(2);
     MAS_LAUNCH_OK("multihot_labels kernels");
+    return 0;
+}
+
+extern "C" size_t mas_dominant_labels_workspace_bytes(int nseg, int num_classes) {
+    if (nseg <= 0 || num_classes <= 0) return 0;
+    return (((size_t)nseg * (num_classes + 1) * sizeof(int32_t) + 255) & ~(size_t)255) + (size_t)nseg;
+}
+
+extern "C" int mas_dominant_labels_dev(const void* ids, int ids_dtype, const uint8_t* target, const uint8_t* keep, int height,
+                                       int width, int nseg, int num_classes, uint8_t* out, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+    MAS_REQUIRE(ids && target && keep && out && workspace, MAS_E_BADARG, "dominant_labels: null pointer");
+    MAS_REQUIRE(height > 0 && width > 0 && nseg > 0 && num_classes > 0 && num_classes < 255, MAS_E_BADARG, "dominant_labels: bad shape");
+    MAS_REQUIRE(ids_dtype == MAS_I32 || ids_dtype == MAS_I64, MAS_E_BADARG, "dominant_labels: bad ids dtype");
+    MAS_REQUIRE(workspace_bytes >= mas_dominant_labels_workspace_bytes(nseg, num_classes), MAS_E_WORKSPACE, "dominant_labels: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t hist_bytes = (size_t)nseg * (num_classes + 1) * sizeof(int32_t);
+    MAS_CUDA_OK(cudaMemsetAsync(workspace, 0, hist_bytes, st));
+    int32_t* hist = reinterpret_cast<int32_t*>(workspace);
+    uint8_t* dom = reinterpret_cast<uint8_t*>(workspace) + ((hist_bytes + 255) & ~(size_t)255);
+    const long long P = (long long)height * width;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)std::min<long long>((P + threads - 1) / threads, (long long)mas::sm_count() * 16);
+    if (ids_dtype == MAS_I64)
+        label_hist_kernel<long long><<<blocks, threads, 0, st>>>(ids, target, height, width, nseg, num_classes, 0, hist);
+    else
+        label_hist_kernel<int32_t><<<blocks, threads, 0, st>>>(ids, target, height, width, nseg, num_classes, 0, hist);
+    dominant_pick_kernel<<<(nseg + threads - 1) / threads, threads, 0, st>>>(hist, keep, nseg, num_classes, dom);
+    if (ids_dtype == MAS_I64)
+        dominant_relabel_kernel<long long><<<blocks, threads, 0, st>>>(ids, target, P, nseg, num_classes, dom, out);
+    else
+        dominant_relabel_kernel<int32_t><<<blocks, threads, 0, st>>>(ids, target, P, nseg, num_classes, dom, out);
+    mas::count_launches(3);
+    MAS_LAUNCH_OK("dominant_labels kernels");
     return 0;
 }

@@ -43,3 +43,23 @@ def assign_all(samples: Iterable[Tuple[torch.Tensor, torch.Tensor, Sequence[int]
         cls_all.append(c.numpy())
         size_all.append(s.numpy().astype(np.int64))
     return np.stack(cls_all).astype("uint8"), np.stack(size_all).astype("int")
+
+
+def dominant_target(target: torch.Tensor, superpixel: torch.Tensor, preserving_labels: Sequence[int], nseg: int,
+                    num_classes: int, device="cuda") -> torch.Tensor:
+    """The "dominant label assignment" block of ``RegionCityscapesDominantAll.__getitem__``
+    (``dataloader/region_dataset.py:221-233``): (H,W) uint8 target in which every listed superpixel carries its most
+    frequent non-ignore train id (ignore pixels stay 255); returned on the CPU like the reference's."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("mulactseg_b200.label_assignment needs a CUDA device (there is no CPU path)")
+    spx = torch.as_tensor(superpixel).to(dev)
+    if spx.dtype not in (torch.int32, torch.int64):
+        spx = spx.long()
+    keep = torch.zeros(nseg, dtype=torch.uint8)
+    ids = [int(p) for p in preserving_labels if 0 <= int(p) < nseg]
+    if ids:
+        keep[torch.as_tensor(ids, dtype=torch.long)] = 1
+    out = ops.dominant_labels(spx.contiguous(), torch.as_tensor(target).to(dev, torch.uint8).contiguous(), keep.to(dev), nseg,
+                              num_classes)
+    return out.cpu()

@@ -357,3 +357,43 @@ def multihot_labels(spx: torch.Tensor, target: torch.Tensor, keep: torch.Tensor,
                   int(nseg), int(num_classes), int(trim_kernel_size), multi_hot.data_ptr(), size.data_ptr(), ws.data_ptr(),
                   need, _stream(spx))
     return multi_hot, size
+
+
+def dominant_labels(spx: torch.Tensor, target: torch.Tensor, keep: torch.Tensor, nseg: int, num_classes: int) -> torch.Tensor:
+    """One image: spx (H,W) i32|i64, target (H,W) u8 train ids (255 = ignore), keep (nseg,) u8 -> relabelled (H,W) u8.
+    See ``mas_dominant_labels_dev``."""
+    _want(spx, "superpixel", (torch.int32, torch.int64), 2)
+    _want(target, "target", torch.uint8, 2)
+    _want(keep, "keep", torch.uint8, 1)
+    if tuple(target.shape) != tuple(spx.shape) or keep.numel() != nseg:
+        raise RuntimeError("dominant_labels: shape mismatch")
+    h, w = spx.shape
+    out = torch.empty_like(target)
+    need = int(_lib.load().mas_dominant_labels_workspace_bytes(int(nseg), int(num_classes)))
+    ws = torch.empty(need, dtype=torch.uint8, device=spx.device)
+    with _on(spx):
+        _lib.call("mas_dominant_labels_dev", spx.data_ptr(), _ids_dtype(spx), target.data_ptr(), keep.data_ptr(), h, w,
+                  int(nseg), int(num_classes), out.data_ptr(), ws.data_ptr(), need, _stream(spx))
+    return out
+
+
+_LABEL_DTYPES = {torch.int64: _lib.MAS_I64, torch.int32: _lib.MAS_I32, torch.uint8: _lib.MAS_U8}
+
+
+def miou_counts(outputs: torch.Tensor, targets: torch.Tensor, num_classes: int, ignore_label: int, by_output: bool,
+                counts: torch.Tensor) -> None:
+    """Accumulate [seen | correct | positive] (3*num_classes int64, device) over two label maps of the same shape."""
+    if not (isinstance(outputs, torch.Tensor) and outputs.is_cuda and isinstance(targets, torch.Tensor) and targets.is_cuda):
+        raise RuntimeError("miou_counts: expected CUDA tensors (there is no CPU path)")
+    if outputs.shape != targets.shape:
+        raise RuntimeError(f"miou_counts: outputs {tuple(outputs.shape)} and targets {tuple(targets.shape)} differ")
+    if outputs.dtype != targets.dtype or outputs.dtype not in _LABEL_DTYPES:
+        outputs, targets = outputs.long(), targets.long()
+    outputs, targets = outputs.contiguous(), targets.contiguous()
+    _want(counts, "counts", torch.int64, 1)
+    if counts.numel() != 3 * num_classes:
+        raise RuntimeError("miou_counts: counts must hold 3 * num_classes int64")
+    with _on(outputs):
+        _lib.call("mas_miou_counts_dev", outputs.data_ptr(), targets.data_ptr(), _LABEL_DTYPES[outputs.dtype], outputs.numel(),
+                  int(num_classes), int(ignore_label), _lib.MAS_MIOU_BY_OUTPUT if by_output else _lib.MAS_MIOU_BY_TARGET,
+                  counts.data_ptr(), _stream(outputs))

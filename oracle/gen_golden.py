@@ -283,6 +283,74 @@ def gen_labelgen():
     print("labelgen.npz", len(out), "arrays")
 
 
+def gen_metrics():
+    """utils/miou.py ``MeanIoU`` (both step hooks, both epoch summaries) and the dominant label assignment of
+    ``RegionCityscapesDominantAll.__getitem__`` (dataloader/region_dataset.py:201-240), both run unmodified (the
+    dataset's file I/O stubbed out like in ``gen_labelgen``)."""
+    miou = importlib.import_module("utils.miou")
+    out = {}
+    for case, (c, ignore, n, h, w, seed) in {"cs19": (19, 255, 3, 24, 40, 61), "voc22_ignore21": (22, 21, 2, 17, 33, 62),
+                                             "tiny": (3, 255, 1, 4, 5, 63)}.items():
+        g = torch.Generator().manual_seed(seed)
+        targets = torch.randint(0, c, (n, h, w), generator=g)
+        outputs = torch.where(torch.rand((n, h, w), generator=g) < 0.6, targets, torch.randint(0, c, (n, h, w), generator=g))
+        targets[torch.rand((n, h, w), generator=g) < 0.15] = ignore
+        outputs[torch.rand((n, h, w), generator=g) < 0.10] = ignore
+        if c > 4:
+            targets[targets == 2] = 3                                  # a class that never occurs in the targets
+            outputs[outputs == 4] = 5                                  # a class that is never predicted
+        out[f"{case}/meta"] = np.asarray([c, ignore], dtype=np.int64)
+        out[f"{case}/outputs"] = outputs.numpy()
+        out[f"{case}/targets"] = targets.numpy()
+        for hook in ("_after_step", "_after_step_within_predregion"):
+            helper = miou.MeanIoU(c, ignore)
+            helper._before_epoch()
+            for i in range(n):                                         # one "batch" per image, like the trainer loop
+                getattr(helper, hook)({"outputs": outputs[i:i + 1], "targets": targets[i:i + 1]})
+            out[f"{case}/{hook}/counts"] = np.stack([helper.total_seen, helper.total_correct, helper.total_positive]).astype(np.int64)
+            out[f"{case}/{hook}/ious"] = np.asarray(helper._after_epoch(), dtype=np.float64)
+            out[f"{case}/{hook}/ious_skip"] = np.asarray(helper._after_epoch(ignore_label_list=[0, c - 1]), dtype=np.float64)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                out[f"{case}/{hook}/ipr"] = np.asarray(helper._after_epoch_ipr(), dtype=np.float64)
+
+    mod = importlib.import_module("dataloader.region_dataset")
+
+    class _FakeImage:
+        def convert(self, *_):
+            return self
+
+    h, w, nseg, c = 40, 64, 24, 7
+    for case, (seed, kind) in {"dominant_jitter": (71, "jitter"), "dominant_random": (72, "random")}.items():
+        spx = synth.superpixel_map(1, h, w, nseg, kind, seed=seed, drop_ids=1)[0]
+        g = torch.Generator().manual_seed(seed)
+        coarse = torch.randint(0, c, (1, 1, h // 4, w // 4), generator=g).float()
+        target = torch.nn.functional.interpolate(coarse, size=(h, w), mode="nearest")[0, 0].long()
+        target[torch.rand((h, w), generator=g) < 0.08] = 255
+        target[spx == 3] = 255                                         # an all-ignore superpixel
+        target[spx == 7] = torch.where(torch.arange(h * w).view(h, w)[spx == 7] % 2 == 0, 4, 1)   # a tie: the smaller id wins
+        ids = sorted(set(torch.unique(spx).tolist()) - {5})            # one id outside the region dict: left as it is
+        ds = mod.RegionCityscapesDominantAll.__new__(mod.RegionCityscapesDominantAll)
+        ds.im_idx = [["img", "lbl", "spx"]]
+        ds.suppix = {"spx": ids}
+        ds.mask_region, ds.return_spx = True, False
+        ds.transform = lambda image, lbls: (image, lbls)
+        ds.open_spx = lambda _f, _spx=spx: _spx.clone()
+        ds.encode_target = lambda t: t
+        saved = mod.Image
+        mod.Image = types.SimpleNamespace(open=lambda f, _t=target: _FakeImage() if f == "img" else _t.numpy().astype(np.uint8).copy())
+        try:
+            got = ds.__getitem__(0)["labels"]
+        finally:
+            mod.Image = saved
+        out[f"{case}/spx"] = spx.numpy().astype(np.int32)
+        out[f"{case}/target"] = target.numpy().astype(np.uint8)
+        out[f"{case}/ids"] = np.asarray(ids, dtype=np.int32)
+        out[f"{case}/meta"] = np.asarray([nseg, c], dtype=np.int32)
+        out[f"{case}/labels"] = np.asarray(got).astype(np.uint8)
+    np.savez_compressed(os.path.join(GOLDEN, "metrics.npz"), **out)
+    print("metrics.npz", len(out), "arrays")
+
+
 def main():
     ref_shims.install()
     os.makedirs(GOLDEN, exist_ok=True)
@@ -292,6 +360,7 @@ def main():
     gen_losses()
     gen_labeller()
     gen_labelgen()
+    gen_metrics()
 
 
 if __name__ == "__main__":
