@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(kAssignThreads) proto_threshold_kernel(LabelPa
                 hist[threadIdx.x] = 0u;     // kAssignThreads == 256
                 __syncthreads();
                 const uint32_t prefix = sel_prefix;
+                const unsigned int rank = sel_rank;         // read by everyone here: the owner lane rewrites it below
                 const int shift = pass < 0 ? 0 : 24 - 8 * pass;
                 for_each(c, [&](float sim) {
                     if (pass < 0) { atomicAdd(&hist[0], 1u); return; }
@@ -407,7 +408,6 @@ __global__ void __launch_bounds__(kAssignThreads) proto_threshold_kernel(LabelPa
                         const unsigned int y = __shfl_up_sync(0xffffffffu, incl, o);
                         if (lane >= o) incl += y;
                     }
-                    const unsigned int rank = sel_rank;
                     const unsigned int owners = __ballot_sync(0xffffffffu, rank < incl);
                     const int owner = owners ? __ffs(owners) - 1 : 31;
                     if (lane == owner) {
