@@ -11,8 +11,8 @@ sharded by image: 372 images per GPU (2975 / 8 rounded up), so N = 8 is the full
 A *step* is one whole round over the resident shard: zero the tables, stream every image's logits through
 the fused scorer (one launch per batch of 4 images, as the selector plugin does), class weights (NCCL
 all-gather of the per-image class-probability sums), per-region scores, per-GPU top-(budget+1) radix
-select, NCCL all-gather of the candidates, merge + sort, copy the winners to the host and cut the prefix
-by cumulative label cost.  ``value`` = regions scored+selected per second over all GPUs.
+select, NCCL all-gather of the candidates, merge + sort, cut the ranked list where the cumulative label cost exceeds
+the budget (on the device) and copy the winners to the host.  ``value`` = regions scored+selected per second over all GPUs.
 
 One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement" for every field.
 """
@@ -224,6 +224,7 @@ def run_ours(args):
     in_pool = torch.ones((n_loc, NSEG), dtype=torch.uint8, device=dev)
     image_rank = torch.arange(rank * n_loc, (rank + 1) * n_loc, dtype=torch.int32, device=dev)
     cost_all = np.random.RandomState(0).randint(1, 4, size=(n_tot * NSEG,)).astype(np.int64)
+    cost_dev = torch.from_numpy(cost_all.astype(np.uint8)).to(dev)      # label cost of every region, indexed like the key's low word
     k_sel = BUDGET + 1
     stats = acq.RegionStats(n_loc, NSEG, C, dev, need_prob=True, lanes=args.lanes)
     ev_pairs = []
@@ -244,9 +245,9 @@ def run_ours(args):
             e1.record()
             ev_pairs.append((e0, e1))
         scores, _ = acq.finalize(stats, spec, COEFF, REF_BATCH, None, [n_loc] * world)
-        keys = selection.top_regions(scores, in_pool, image_rank, k_sel, None)   # host uint64, sorted descending
-        tie = (keys & np.uint64(0xFFFFFFFF)).astype(np.int64)                    # == global region index here
-        return selection.cumulative_cut(cost_all[tie], BUDGET)
+        # ranked keys on the host (uint64, descending), already cut where expand_training_set stops
+        keys = selection.top_regions(scores, in_pool, image_rank, k_sel, None, cost_dev, BUDGET)
+        return len(keys)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -256,6 +257,30 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         picked = step(False)
+    sync_all()
+
+    def phases():
+        """One extra, untimed round with a device sync after every phase: where a round's time goes (wall clock, ms)."""
+        marks = []
+
+        def mark(name):
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
+        mark("start")
+        stats.zero_()
+        mark("zero_tables")
+        for i in range(0, n_loc, REF_BATCH):
+            stats.add_batch(i, logits[i:i + REF_BATCH], spx[i:i + REF_BATCH], TEMP)
+        stats.join()
+        mark("score")
+        scores, _ = acq.finalize(stats, spec, COEFF, REF_BATCH, None, [n_loc] * world)
+        mark("class_weights+region_scores")
+        selection.top_regions(scores, in_pool, image_rank, k_sel, None, cost_dev, BUDGET)
+        mark("top_regions(select+sort+budget_cut+d2h)")
+        return {b[0]: round(1e3 * (b[1] - a[1]), 3) for a, b in zip(marks, marks[1:])}
+
+    phase_ms = phases() if world == 1 else None
     sync_all()
     launches0 = lib.mas_kernel_launches()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -354,7 +379,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": workload_config(args, n_loc), "roofline": roofline, "cpu_baseline": cpu,
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "wall_ms_per_step": 1e3 * wall / args.steps,
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "phases_ms_synced": phase_ms, "wall_ms_per_step": 1e3 * wall / args.steps,
                 "selected_regions": int(picked)}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -80,6 +80,15 @@ int mas_bvsb_segment_stats_dev(const void* logits, int logits_dtype, int64_t ima
                                float* cls_sum, int32_t* cls_cnt, double* prob_sum,
                                void* stream);
 
+/* mas_class_weights_dev -- w_c = (coeff * pbar_c + 1)^-2, pbar = the reference's `cumulated_pred_prob / len(loader)`
+ * (active_selection/my_bvsb_predclsbal_pwr.py:33-47): per reference batch of `ref_batch` images (the last may be short)
+ * the mean probability of class c = sum of prob_sum rows / (images * pixels_per_image), accumulated over the batches in
+ * loader order in fp32.  prob_sum (n_img, channels) f64 from mas_bvsb_segment_stats_dev (all ranks' rows in pool order),
+ * weight: channels DEVICE floats -- the `class_weight` argument of mas_region_scores_dev.
+ */
+int mas_class_weights_dev(const double* prob_sum, int64_t n_img, int channels, int64_t pixels_per_image, int ref_batch,
+                          float coeff, float* weight, void* stream);
+
 /* mas_region_scores_dev -- per-region epilogue over the tables above.
  *   n[r]        = sum_c cls_cnt[r][c]
  *   score[r]    = (sum_c w[c] * cls_sum[r][c]) / max(n[r], 1)     (w == NULL -> all ones)
@@ -157,6 +166,15 @@ int mas_topk_sorted_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t
  */
 int mas_topk_candidates_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int64_t capacity,
                                 int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* mas_prefix_cut_dev -- how much of the ranked list RegionActiveDataset.expand_training_set consumes
+ * (dataloader/region_active_dataset.py:56-66): walk sorted_keys[0 .. *count), add cost_by_tie[key & 0xffffffff] (the label
+ * cost of the region: 1, or its multi-hot class count with --fair_counting --or_labeling) and stop AFTER the pick that
+ * makes the running cost exceed `budget` (strict '>').  *n_take = that prefix length (the whole list if the budget is
+ * never exceeded; -1 if *count is -1).  cost_by_tie: n_cost uint8, indexed like the low key word (image rank * nseg + id).
+ */
+int mas_prefix_cut_dev(const uint64_t* sorted_keys, const int32_t* count, const uint8_t* cost_by_tie, int64_t n_cost,
+                       int64_t budget, int32_t* n_take, void* stream);
 
 /* ------------------------------------------------------------------ host-buffer entries (end-to-end)
  *

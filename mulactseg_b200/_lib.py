@@ -29,6 +29,8 @@ SIGNATURES = {
     "mas_kernel_launches": (c_int64, []),
     "mas_bvsb_segment_stats_dev": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                                            c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mas_class_weights_dev": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int, c_float, c_void_p, c_void_p]),
+    "mas_prefix_cut_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "mas_region_scores_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mas_minmax_nonzero_dev": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "mas_dominant_hist_dev": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),

@@ -148,7 +148,10 @@ def finalize(stats: RegionStats, spec: SelectorSpec, coeff: float = 0.0, ref_bat
         if stats.prob_sum is None:
             raise RuntimeError("predclsbal weighting needs RegionStats(need_prob=True)")
         prob_all = mdist.all_gather_rows(stats.prob_sum, group, shard_counts)
-        weight = predicted_class_weights(prob_all, stats.pixels_per_image, ref_batch, coeff).contiguous()
+        if prob_all.is_cuda:
+            weight = ops.class_weights(prob_all.contiguous(), stats.pixels_per_image, ref_batch, coeff)
+        else:       # gloo / CPU tensors in the host-logic tests
+            weight = predicted_class_weights(prob_all, stats.pixels_per_image, ref_batch, coeff).contiguous()
     score, _, dominant = ops.region_scores(stats.cls_sum, stats.cls_cnt, weight)
     minmax = None
     if spec.normalise:

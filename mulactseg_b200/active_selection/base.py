@@ -114,23 +114,22 @@ class RegionSelector(object):
         scores = mdist.all_gather_rows(ps.scores, self.group)
         return self.gen_score_list_from_tensor(pool_set, scores)
 
-    def ranked_prefix(self, ps: PoolScores, pool_set, k: int):
-        """The first ``k`` entries of ``sorted(calculate_scores(...), reverse=True)`` without building the list."""
+    def ranked_prefix(self, ps: PoolScores, pool_set, k: int, cost_table=None, budget=None):
+        """The first ``k`` entries of ``sorted(calculate_scores(...), reverse=True)`` without building the list; with a
+        device cost table (``selection.region_cost_table``) and a budget, cut where ``expand_training_set`` stops."""
         device = ps.scores.device
         rank = selection.image_ranks(pool_set.im_idx)
         mask = selection.pool_mask(pool_set.im_idx, pool_set.suppix, ps.nseg, ps.lo, ps.hi)
         keys = selection.top_regions(ps.scores, torch.from_numpy(mask).to(device),
-                                     torch.from_numpy(rank[ps.lo:ps.hi].copy()).to(device), k, self.group)
+                                     torch.from_numpy(rank[ps.lo:ps.hi].copy()).to(device), k, self.group, cost_table, budget)
         return selection.decode_keys(keys, ps.nseg, pool_set.im_idx, rank)
 
-    def _region_costs(self, active_set, prefix):
-        """Multi-hot class count per region when --fair_counting --or_labeling (region_active_dataset.py:56-61)."""
+    def _pool_costs(self, active_set, pool_set):
+        """(N, S) multi-hot class count of every pool region when --fair_counting --or_labeling
+        (region_active_dataset.py:56-61: ``multi_hot_cls[trg_index, suppix_id].sum()``), in pool order."""
         lab = active_set.trg_label_dataset
-        costs = np.empty(len(prefix), dtype=np.int64)
-        for n, (_, joined, sid) in enumerate(prefix):
-            stem = joined.split(",")[2].split("/")[-1].split(".")[0]
-            costs[n] = int(lab.multi_hot_cls[lab.id_to_index[stem], sid].sum())
-        return costs
+        rows = [lab.id_to_index[key[2].split("/")[-1].split(".")[0]] for key in pool_set.im_idx]
+        return np.asarray(lab.multi_hot_cls)[np.asarray(rows, dtype=np.int64)].sum(axis=-1)
 
     def select_next_batch(self, trainer, active_set, selection_count):
         pool_set = active_set.trg_pool_dataset
@@ -145,11 +144,18 @@ class RegionSelector(object):
         n_pool = sum(len(v) for v in pool_set.suppix.values())
         fair = getattr(active_set.args, "fair_counting", False) and getattr(active_set.args, "or_labeling", False)
         k = min(int(selection_count) + 1, n_pool)
+        cost_table = costs = None
+        if fair:
+            # label cost of every pool region as a device table: the ranked list is cut on the GPU where the walk of
+            # expand_training_set stops, and only that prefix is decoded into python tuples
+            costs = self._pool_costs(active_set, pool_set)
+            cost_table = selection.region_cost_table(costs, selection.image_ranks(pool_set.im_idx), ps.scores.device)
         while True:
-            prefix = self.ranked_prefix(ps, pool_set, k)
-            if k >= n_pool or not fair:
+            prefix = self.ranked_prefix(ps, pool_set, k, cost_table, selection_count if fair else None)
+            if k >= n_pool or not fair or len(prefix) < k:
                 break
-            if self._region_costs(active_set, prefix).sum() > selection_count:
+            index_of = {",".join(key): i for i, key in enumerate(pool_set.im_idx)}
+            if sum(int(costs[index_of[joined], sid]) for _, joined, sid in prefix) > selection_count:
                 break
             k = min(2 * k, n_pool)   # zero-cost regions: the walk needs a longer prefix
         active_set.expand_training_set(prefix, selection_count, self.active_method)

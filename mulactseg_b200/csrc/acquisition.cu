@@ -88,7 +88,39 @@ __global__ void finalize_scores_kernel(float* __restrict__ score, const int32_t*
     score[i] = u;
 }
 
+// w_c = (coeff * pbar_c + 1)^-2 with pbar = mean over the reference's batches of the per-batch mean probability:
+// `cumulated += mean(prob, dim=(0,2,3))` per batch in loader order, fp32, then `/ len(loader)`
+// (active_selection/my_bvsb_predclsbal_pwr.py:36-47).  One thread per class walks the batches in that order.
+__global__ void class_weights_kernel(const double* __restrict__ prob_sum, long long n_img, int C, double pixels, int ref_batch,
+                                     float coeff, float* __restrict__ weight) {
+    const int c = threadIdx.x;
+    if (c >= C) return;
+    float cumulated = 0.f;
+    long long n_batches = 0;
+    for (long long b0 = 0; b0 < n_img; b0 += ref_batch, ++n_batches) {
+        const int len = (int)min((long long)ref_batch, n_img - b0);
+        double s = 0.0;
+        for (int i = 0; i < len; ++i) s += prob_sum[(b0 + i) * C + c];
+        cumulated += (float)(s / ((double)len * pixels));
+    }
+    const float pbar = cumulated / (float)n_batches;
+    const float x = coeff * pbar + 1.f;
+    weight[c] = 1.f / (x * x);
+}
+
 }  // namespace
+
+extern "C" int mas_class_weights_dev(const double* prob_sum, int64_t n_img, int channels, int64_t pixels_per_image, int ref_batch,
+                                     float coeff, float* weight, void* stream) {
+    MAS_REQUIRE(prob_sum && weight, MAS_E_BADARG, "class_weights: null pointer");
+    MAS_REQUIRE(n_img > 0 && pixels_per_image > 0 && ref_batch > 0, MAS_E_BADARG, "class_weights: bad size");
+    MAS_REQUIRE(channels >= 1 && channels <= MAS_MAX_CLASSES, MAS_E_RANGE, "class_weights: channels out of range");
+    class_weights_kernel<<<1, MAS_MAX_CLASSES, 0, (cudaStream_t)stream>>>(prob_sum, n_img, channels, (double)pixels_per_image,
+                                                                         ref_batch, coeff, weight);
+    mas::count_launches(1);
+    MAS_LAUNCH_OK("class_weights_kernel");
+    return 0;
+}
 
 extern "C" int mas_region_scores_dev(const float* cls_sum, const int32_t* cls_cnt, const float* class_weight,
                                      int64_t n_regions, int channels, float* score, int32_t* npix, int32_t* dominant,

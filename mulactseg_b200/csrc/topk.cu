@@ -187,6 +187,59 @@ __global__ void fast_finish_kernel(const FastState* st, int32_t* out_count, long
     *out_count = c > capacity ? -1 : (int32_t)(clamp ? min(c, k) : c);
 }
 
+// ---------------------------------------------------------------------------------------- budget cut
+// RegionActiveDataset.expand_training_set walks the sorted list and stops AFTER the pick that makes the running label
+// cost exceed the budget (strict '>', dataloader/region_active_dataset.py:56-66).  One CTA: gather the cost of every
+// ranked region, block-wide inclusive scan with a running carry, first index over the budget.
+constexpr int kCutThreads = 1024;
+constexpr int kCutPer = 4;
+
+__global__ void __launch_bounds__(kCutThreads) prefix_cut_kernel(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ count,
+                                                                 const uint8_t* __restrict__ cost_by_tie, long long n_cost,
+                                                                 long long budget, int32_t* __restrict__ n_take) {
+    __shared__ long long warp_tot[kCutThreads / 32];
+    __shared__ long long carry;
+    __shared__ int first;
+    const int n = *count;
+    if (n < 0) { if (threadIdx.x == 0) *n_take = -1; return; }
+    if (threadIdx.x == 0) { carry = 0; first = n; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += kCutThreads * kCutPer) {
+        const int i0 = base + threadIdx.x * kCutPer;
+        int c[kCutPer];
+        long long mine = 0;
+#pragma unroll
+        for (int j = 0; j < kCutPer; ++j) {
+            const int i = i0 + j;
+            long long tie = i < n ? (long long)(keys[i] & 0xffffffffull) : -1;
+            c[j] = (tie >= 0 && tie < n_cost) ? (int)cost_by_tie[tie] : 0;
+            mine += c[j];
+        }
+        long long incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        long long before = carry + incl - mine;
+        for (int w = 0; w < warp; ++w) before += warp_tot[w];
+        long long running = before;
+#pragma unroll
+        for (int j = 0; j < kCutPer; ++j) {
+            running += c[j];
+            if (i0 + j < n && running > budget) { atomicMin(&first, i0 + j); break; }
+        }
+        __syncthreads();
+        if (threadIdx.x == kCutThreads - 1) carry = before + mine;
+        __syncthreads();
+        if (first < n) break;
+    }
+    if (threadIdx.x == 0) *n_take = first < n ? first + 1 : n;
+}
+
 // ---------------------------------------------------------------------------------------- bitonic sort (descending)
 constexpr int kSortThreads = 1024;
 constexpr int kSortTile = 8192;            // keys per CTA: 64 KB of shared memory, 4 comparators per thread and step
@@ -388,5 +441,16 @@ extern "C" int mas_topk_sorted_u64_dev(const uint64_t* keys, int64_t n, int64_t 
     const int rc = fast_candidates("topk_sorted_u64", keys, n, k, out, capacity, out_count, workspace, workspace_bytes, stream, true);
     if (rc != 0) return rc;
     if (n > 0 && k > 0) return mas_sort_desc_u64_dev(out, capacity, stream);
+    return 0;
+}
+
+extern "C" int mas_prefix_cut_dev(const uint64_t* sorted_keys, const int32_t* count, const uint8_t* cost_by_tie, int64_t n_cost,
+                                  int64_t budget, int32_t* n_take, void* stream) {
+    MAS_REQUIRE(sorted_keys && count && cost_by_tie && n_take, MAS_E_BADARG, "prefix_cut: null pointer");
+    MAS_REQUIRE(n_cost >= 0 && n_cost <= (1ll << 32), MAS_E_BADARG, "prefix_cut: bad table size");
+    prefix_cut_kernel<<<1, kCutThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(sorted_keys), count,
+                                                                  cost_by_tie, n_cost, budget, n_take);
+    mas::count_launches(1);
+    MAS_LAUNCH_OK("prefix_cut_kernel");
     return 0;
 }

@@ -88,6 +88,30 @@ def bvsb_segment_stats(logits: torch.Tensor, spx: torch.Tensor, nseg: int, tempe
                   _ptr(prob_sum), _stream(logits))
 
 
+def class_weights(prob_sum: torch.Tensor, pixels_per_image: int, ref_batch: int, coeff: float) -> torch.Tensor:
+    """(N,C) f64 per-image probability sums in pool order -> (C,) f32 class weights (``mas_class_weights_dev``)."""
+    _want(prob_sum, "prob_sum", torch.float64, 2)
+    n, c = prob_sum.shape
+    weight = torch.empty(c, dtype=torch.float32, device=prob_sum.device)
+    with _on(prob_sum):
+        _lib.call("mas_class_weights_dev", prob_sum.data_ptr(), n, c, int(pixels_per_image), max(int(ref_batch), 1), float(coeff),
+                  weight.data_ptr(), _stream(prob_sum))
+    return weight
+
+
+def prefix_cut(sorted_keys: torch.Tensor, count: torch.Tensor, cost_by_tie: torch.Tensor, budget: int) -> torch.Tensor:
+    """Device int32: length of the prefix of the ranked list whose running cost first exceeds ``budget``
+    (``mas_prefix_cut_dev``)."""
+    _want(sorted_keys, "sorted_keys", torch.int64, 1)
+    _want(count, "count", torch.int32, 1)
+    _want(cost_by_tie, "cost_by_tie", torch.uint8, 1)
+    n_take = torch.empty(1, dtype=torch.int32, device=sorted_keys.device)
+    with _on(sorted_keys):
+        _lib.call("mas_prefix_cut_dev", sorted_keys.data_ptr(), count.data_ptr(), cost_by_tie.data_ptr(), cost_by_tie.numel(),
+                  int(budget), n_take.data_ptr(), _stream(sorted_keys))
+    return n_take
+
+
 def region_scores(cls_sum: torch.Tensor, cls_cnt: torch.Tensor, class_weight: Optional[torch.Tensor] = None,
                   want_npix: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
     """(score, npix | None, dominant), each shaped like cls_sum without its last dim."""

@@ -61,12 +61,16 @@ def decode_keys(keys: np.ndarray, nseg: int, im_idx: Sequence[Sequence[str]], ra
     return out
 
 
-def top_regions(scores: torch.Tensor, in_pool: torch.Tensor, image_rank_local: torch.Tensor, k: int, group=None):
+def top_regions(scores: torch.Tensor, in_pool: torch.Tensor, image_rank_local: torch.Tensor, k: int, group=None,
+                cost_by_tie: Optional[torch.Tensor] = None, budget: Optional[int] = None):
     """Sorted (descending) keys of the k best pool regions over ALL ranks, as a host uint64 array.
 
     scores / in_pool: this rank's (n_local, S) shard; image_rank_local: global ranks of its images.
     Per rank: key -> candidate superset of its k best (<= sort_capacity(k) slots) -> all_gather -> select + sort k on
     every rank; no host sync before the final count.
+    With ``cost_by_tie`` (uint8 device table of label costs indexed by image rank * S + id, see ``region_cost_table``)
+    and ``budget`` the list is cut on the device where ``expand_training_set`` would stop (``mas_prefix_cut_dev``) and
+    only that prefix travels to the host.
     """
     local_keys = ops.region_keys(scores, in_pool, image_rank_local)
     distributed = mdist.is_distributed(group)
@@ -77,7 +81,8 @@ def top_regions(scores: torch.Tensor, in_pool: torch.Tensor, image_rank_local: t
         worst = mdist.all_reduce_min(count.to(torch.int64), group)       # -1 if the buffer overflowed on any rank
         keys = mdist.gather_candidates(local, count, local.numel(), group)
     best, count = ops.topk_sorted(keys, k)           # two bucket histograms + compaction + sort
-    n = int(count.item())
+    take = ops.prefix_cut(best, count, cost_by_tie, budget) if cost_by_tie is not None else count
+    n = int(take.item())
     if n < 0 or (worst is not None and int(worst.item()) < 0):
         # massively tied scores overflowed a candidate buffer somewhere: every rank redoes the exact radix select
         keys = local_keys
@@ -85,8 +90,17 @@ def top_regions(scores: torch.Tensor, in_pool: torch.Tensor, image_rank_local: t
             local, count = ops.topk_keys(local_keys, k, sort=False)
             keys = mdist.gather_candidates(local, count, k, group)
         best, count = ops.topk_keys(keys, k, sort=True)
-        n = int(count.item())
+        take = ops.prefix_cut(best, count, cost_by_tie, budget) if cost_by_tie is not None else count
+        n = int(take.item())
     return best[:n].cpu().numpy().view(np.uint64)
+
+
+def region_cost_table(costs_by_image: np.ndarray, rank: np.ndarray, device) -> torch.Tensor:
+    """(N, S) label costs in pool order -> flat uint8 device table indexed by image RANK * S + id (the low key word)."""
+    n, s = costs_by_image.shape
+    table = np.empty((n, s), dtype=np.uint8)
+    table[np.asarray(rank, dtype=np.int64)] = np.minimum(costs_by_image, 255).astype(np.uint8)
+    return torch.from_numpy(table.reshape(-1)).to(device)
 
 
 def cumulative_cut(costs: np.ndarray, budget: int) -> int:

@@ -251,6 +251,63 @@ def test_plugin_select_next_batch_matches_oracle(method, predignore, tmp_path):
         assert [(p, i) for _, p, i in picked["ranked"][: budget + 1]] == [(p, i) for _, p, i in ref_sorted[: budget + 1]]
 
 
+@pytest.mark.parametrize("n,budget,zero_frac", [(1000, 300, 0.0), (5000, 20000, 0.0), (100001, 100000, 0.0), (3000, 50, 0.9),
+                                               (10, 0, 0.0), (1, 5, 0.0)])
+def test_prefix_cut_matches_numpy(n, budget, zero_frac):
+    """mas_prefix_cut_dev == the strict '>' walk of expand_training_set (numpy: selection.cumulative_cut)."""
+    from mulactseg_b200 import ops, selection
+    rng = np.random.RandomState(n + budget)
+    n_cost = 4 * n + 7
+    table = rng.randint(1, 5, size=n_cost).astype(np.uint8)
+    table[rng.rand(n_cost) < zero_frac] = 0
+    ties = rng.permutation(n_cost)[:n].astype(np.uint64)
+    keys = ((np.arange(n, 0, -1).astype(np.uint64) << np.uint64(32)) | ties).view(np.int64)     # already descending
+    buf = torch.zeros(ops.sort_capacity(n), dtype=torch.int64, device=DEV)
+    buf[:n] = torch.from_numpy(keys).to(DEV)
+    got = int(ops.prefix_cut(buf, torch.tensor([n], dtype=torch.int32, device=DEV), torch.from_numpy(table).to(DEV), budget).item())
+    assert got == selection.cumulative_cut(table[ties.astype(np.int64)], budget)
+    assert int(ops.prefix_cut(buf, torch.tensor([-1], dtype=torch.int32, device=DEV), torch.from_numpy(table).to(DEV), budget).item()) == -1
+
+
+@pytest.mark.parametrize("zero_cost_frac,budget", [(0.0, 30), (0.6, 25), (1.0, 10)])
+def test_plugin_fair_counting_cut_matches_oracle(zero_cost_frac, budget):
+    """--fair_counting --or_labeling: the plugin cuts the ranked list on the device by multi-hot class counts; the
+    reference walk (oracle expand_training_set with the same costs) consumes exactly that prefix."""
+    import types
+    n, c, h, w, nseg, bs = 6, 8, 48, 64, 24, 2
+    logits = synth.logits(n, c, h, w, "cosine", seed=25)
+    spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=26)
+    im_idx, suppix = synth.pool_lists(n, nseg, spx, labelled_frac=0.1, seed=28)
+    args = selector_args("my_bvsb_predclsbal_pwr_banignore", nseg, c - 1, True, 0.1, 6.0, bs)
+    selector = importlib.import_module("mulactseg_b200.active_selection.my_bvsb_predclsbal_pwr_banignore").RegionSelector(args)
+    g = torch.Generator().manual_seed(29)
+    multi_hot = (torch.rand((n + 2, nseg, c), generator=g) < 0.25).to(torch.uint8)
+    multi_hot[(torch.rand((n + 2, nseg), generator=g) < zero_cost_frac)] = 0          # zero-cost regions: the prefix must grow
+    order = torch.randperm(n + 2, generator=g).tolist()                                  # label rows are not in pool order
+    stem = lambda key: key[2].split("/")[-1].split(".")[0]
+    label = types.SimpleNamespace(im_idx=[], suppix={}, multi_hot_cls=multi_hot.numpy(),
+                                  id_to_index={stem(k): order[i] for i, k in enumerate(im_idx)})
+    pool_ds = PoolSet(logits, spx.long(), im_idx, suppix)
+    scores = selector.calculate_scores(fake_trainer(DEV), PoolSet(logits, spx.long(), im_idx, suppix))
+    cost = lambda spx_path, sid: int(label.multi_hot_cls[label.id_to_index[spx_path.split("/")[-1].split(".")[0]], sid].sum())
+    seen = {}
+
+    class ActiveSet:
+        args = types.SimpleNamespace(fair_counting=True, or_labeling=True)
+        trg_pool_dataset = pool_ds
+        trg_label_dataset = label
+
+        def expand_training_set(self, ranked, count, name):
+            seen["ranked"] = list(ranked)
+            seen["n"] = oa.expand_training_set(ranked, count, label.im_idx, label.suppix, pool_ds.im_idx, pool_ds.suppix, cost)
+
+    selector.select_next_batch(fake_trainer(DEV), ActiveSet(), budget)
+    full = sorted(scores, reverse=True)
+    want_n = oa.expand_training_set(full, budget, [], {}, [list(k) for k in im_idx], {k: list(v) for k, v in suppix.items()}, cost)
+    assert seen["n"] == want_n == len(seen["ranked"])                 # handed exactly the prefix the walk consumes
+    assert [(p, i) for _, p, i in seen["ranked"]] == [(p, i) for _, p, i in full[:want_n]]
+
+
 def test_host_entry_matches_device_path():
     from mulactseg_b200 import _lib
     n, c, h, w, nseg = 5, 20, 64, 128, 96
