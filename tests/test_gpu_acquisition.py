@@ -131,6 +131,34 @@ def test_full_size_properties(path, stages, warps, monkeypatch):
     assert torch.equal(stats2.cls_cnt, stats.cls_cnt.view(n, nseg // 2, 2, c).sum(dim=2).int())
 
 
+@pytest.mark.parametrize("shape", [(4, 22, 513, 513, 150), (3, 21, 375, 500, 150)])
+def test_voc_size_properties(shape):
+    """BASELINE config 3 shapes (odd width -> scalar loads; 500 x 375 native): the same size-independent invariants."""
+    from mulactseg_b200 import acquisition as acq
+    n, c, h, w, nseg = shape
+    logits = synth.logits(n, c, h, w, "cosine", seed=3, device=DEV)
+    spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=4, device=DEV, dtype=torch.int32, drop_ids=3)
+    stats = acq.RegionStats(n, nseg, c, DEV, need_prob=True)
+    stats.add_batch(0, logits[:3], spx[:3], 0.1)               # a batch of 3 and, when there is one, a short last batch
+    if n > 3:
+        stats.add_batch(3, logits[3:], spx[3:], 0.1)
+    cnt = stats.cls_cnt.long()
+    assert cnt.sum(dim=(1, 2)).tolist() == [h * w] * n
+    top1 = logits.argmax(dim=1)
+    for i in range(n):
+        assert torch.equal(cnt[i].sum(dim=1), torch.bincount(spx[i].reshape(-1).long(), minlength=nseg))
+        assert torch.equal(cnt[i].sum(dim=0), torch.bincount(top1[i].reshape(-1), minlength=c))
+    np.testing.assert_allclose(stats.prob_sum.sum(dim=1).cpu().numpy(), [h * w] * n, rtol=1e-6)
+    top2 = logits.topk(2, dim=1).values
+    bvsb = torch.exp((top2[:, 1] - top2[:, 0]).double() / 0.1) + 1e-8
+    np.testing.assert_allclose(stats.cls_sum.double().sum(dim=(1, 2)).cpu().numpy(), bvsb.sum(dim=(1, 2)).cpu().numpy(), rtol=1e-5)
+    # the ban-ignore selector end to end on this shape: banned regions are exactly those dominated by the last channel
+    score, dom = acq.finalize(stats, acq.SELECTORS["my_bvsb_predclsbal_pwr_banignore"], 12.0, 4)
+    dominant = cnt.argmax(dim=2)
+    assert torch.equal(dom.long(), dominant)
+    assert float(score[dominant == c - 1].abs().max() if (dominant == c - 1).any() else 0.0) == 0.0
+
+
 def test_ids_outside_range_are_ignored_and_empty_batch():
     from mulactseg_b200 import acquisition as acq
     n, c, h, w, nseg = 1, 6, 16, 32, 5
