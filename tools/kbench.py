@@ -54,6 +54,9 @@ def main():
             torch.cuda.synchronize()
         return
     variants = [("tma", {}), ("tma_1lane", {"LANES": "1"}), ("ldg", {"MAS_SCORER_PATH": "ldg"})]
+    if os.environ.get("KBENCH_EXTRA"):
+        variants = [("tma", {}), ("tma_w4", {"MAS_SCORER_WARPS": "4"}), ("tma_w4_3lanes", {"MAS_SCORER_WARPS": "4", "LANES": "3"}),
+                    ("tma_w2", {"MAS_SCORER_WARPS": "2"}), ("tma_w4_s3", {"MAS_SCORER_WARPS": "4", "MAS_SCORER_STAGES": "3"})]
     if not args.quick:
         variants += [("tma_s3_w6", {"MAS_SCORER_STAGES": "3", "MAS_SCORER_WARPS": "6"}),
                      ("tma_s2_w6", {"MAS_SCORER_WARPS": "6"})]
