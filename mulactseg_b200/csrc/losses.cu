@@ -90,7 +90,7 @@ __device__ __forceinline__ int load_id(const void* ids, size_t i) {
 // Only the few candidate classes of a pixel ever need P_c, so the C' normalisations are not done here.
 template <int CMAX, bool ACCURATE>
 __device__ __forceinline__ float softmax_numerators(float (&v)[CMAX], float temp, float scale) {
-    if (ACCURATE) {
+    if (ACCURATE && temp != 1.f) {      // x / 1.0f == x: the stage-2 labeller (T = 1, :140) skips the C' divisions
 #pragma unroll
         for (int c = 0; c < CMAX; ++c) v[c] = __fdiv_rn(v[c], temp);   // padded planes hold -inf
     }
