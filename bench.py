@@ -34,8 +34,19 @@ import torch  # noqa: E402
 
 H, W, C, NSEG = 1024, 2048, 19, 2048
 TEMP, COEFF, REF_BATCH, BUDGET = 0.1, 6.0, 4, 100_000
+METHOD, BAN_IGNORE, POOL_IMAGES, GRID = "my_bvsb_predclsbal_pwr", False, 2975, "32x64"
+WORKLOAD = "configs[1]: my_bvsb_predclsbal_pwr acquisition round, synthetic Cityscapes-shaped pool"
 METRIC = "superpixel regions scored+selected/sec"
 UNIT = "regions/s"
+
+
+def use_voc_workload():
+    """BASELINE.json configs[2] (not the contract's default line): VOC-shaped pool, 10 582 images of 375x500 (native shape),
+    21 classes + the predicted-ignore channel, 150 superpixels, the _banignore selector, cls_weight_coeff 12, budget 10 000."""
+    global H, W, C, NSEG, COEFF, BUDGET, METHOD, BAN_IGNORE, POOL_IMAGES, GRID, WORKLOAD
+    H, W, C, NSEG, COEFF, BUDGET = 375, 500, 22, 150, 12.0, 10_000
+    METHOD, BAN_IGNORE, POOL_IMAGES, GRID = "my_bvsb_predclsbal_pwr_banignore", True, 10582, "10x15"
+    WORKLOAD = "configs[2]: my_bvsb_predclsbal_pwr_banignore acquisition round, synthetic PASCAL-VOC-shaped pool"
 
 
 def parse():
@@ -44,11 +55,14 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--images-per-gpu", type=int, default=372)
+    ap.add_argument("--workload", default="cityscapes", choices=["cityscapes", "voc"],
+                    help="cityscapes = BASELINE configs[1] (the contract line); voc = configs[2], 1323 images per GPU")
+    ap.add_argument("--images-per-gpu", type=int, default=0, help="0 = pool / 8 rounded up (372 Cityscapes, 1323 VOC)")
     ap.add_argument("--e2e-images", type=int, default=24, help="images per GPU in the host-buffer (e2e) step")
     ap.add_argument("--cpu-images", type=int, default=128, help="images in the bounded CPU-baseline sample (16 distinct images, cycled)")
     ap.add_argument("--coherent", type=int, default=0, help="draw logits at 1/k resolution and up-sample (0 = i.i.d.)")
     ap.add_argument("--lanes", type=int, default=2, help="side streams the scorer launches alternate over (1 = caller's stream only)")
+    ap.add_argument("--group-mb", type=int, default=1536, help="logits queued per scorer launch (MB; 0 = one launch per batch of 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -142,11 +156,11 @@ def cpu_round(n_img: int, seed: int = 0, inputs=None):
     n_img = sum(b[0].shape[0] for b in pool)
     im_idx, cost = im_idx[:n_img], cost[:n_img]
     t0 = time.perf_counter()
-    scores = oa.scores_predclsbal_pwr(pool, NSEG, TEMP, COEFF, ban_ignore=False)
+    scores = oa.scores_predclsbal_pwr(pool, NSEG, TEMP, COEFF, ban_ignore=BAN_IGNORE)
     t1 = time.perf_counter()
     ranked = oa.rank_regions(oa.score_list(im_idx, suppix, scores))
     t2 = time.perf_counter()
-    budget = max(1, int(BUDGET * n_img / 2975))
+    budget = max(1, int(BUDGET * n_img / POOL_IMAGES))
     oa.expand_training_set(ranked, budget, [], {}, [list(k) for k in im_idx], {k: list(v) for k, v in suppix.items()},
                            lambda p, s: cost[index_of[p], s])
     t3 = time.perf_counter()
@@ -184,11 +198,11 @@ def run_reference(args):
 
 
 def workload_config(args, images_per_gpu, note=""):
-    return {"workload": "configs[1]: my_bvsb_predclsbal_pwr acquisition round, synthetic Cityscapes-shaped pool",
+    return {"workload": WORKLOAD,
             "images_per_gpu": images_per_gpu, "height": H, "width": W, "classes": C, "nseg": NSEG,
             "val_batch_size": REF_BATCH, "cls_weight_coeff": COEFF, "temperature": TEMP, "budget": BUDGET,
             "fair_counting": True, "logits": "tanh(N(0,1))*0.9" + (f", coherent/{args.coherent}" if args.coherent else ", i.i.d."),
-            "superpixels": "jittered 32x64 grid", "sharding": f"by image, dp{args.gpus}",
+            "superpixels": f"jittered {GRID} grid", "sharding": f"by image, dp{args.gpus}",
             "l2": "inputs (>= 4 GB per GPU) exceed the 126 MB L2; no flush needed", "note": note}
 
 
@@ -210,7 +224,7 @@ def run_ours(args):
     n_loc = args.images_per_gpu
     n_tot = n_loc * world
     P = H * W
-    spec = acq.SELECTORS["my_bvsb_predclsbal_pwr"]
+    spec = acq.SELECTORS[METHOD]
 
     # ---- resident inputs (generated on the device, per chunk to bound temporaries)
     logits = torch.empty((n_loc, C, H, W), dtype=torch.float32, device=dev)
@@ -226,9 +240,9 @@ def run_ours(args):
     cost_all = np.random.RandomState(0).randint(1, 4, size=(n_tot * NSEG,)).astype(np.int64)
     cost_dev = torch.from_numpy(cost_all.astype(np.uint8)).to(dev)      # label cost of every region, indexed like the key's low word
     k_sel = BUDGET + 1
-    stats = acq.RegionStats(n_loc, NSEG, C, dev, need_prob=True, lanes=args.lanes)
+    stats = acq.RegionStats(n_loc, NSEG, C, dev, need_prob=True, lanes=args.lanes, group_bytes=args.group_mb << 20)
     ev_pairs = []
-    n_launch = (n_loc + REF_BATCH - 1) // REF_BATCH
+    launches_seen = []
 
     def step(record_events: bool):
         stats.zero_()
@@ -238,12 +252,14 @@ def run_ours(args):
         if record_events:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+            l0 = stats.launches
         for i in range(0, n_loc, REF_BATCH):
-            stats.add_batch(i, logits[i:i + REF_BATCH], spx[i:i + REF_BATCH], TEMP)
+            stats.add_batch(i, logits[i:i + REF_BATCH], spx[i:i + REF_BATCH], TEMP)    # one call per loader batch, like the plugin
         if record_events:
             stats.join()
             e1.record()
             ev_pairs.append((e0, e1))
+            launches_seen.append(stats.launches - l0)
         scores, _ = acq.finalize(stats, spec, COEFF, REF_BATCH, None, [n_loc] * world)
         # ranked keys on the host (uint64, descending), already cut where expand_training_set stops
         keys = selection.top_regions(scores, in_pool, image_rank, k_sel, None, cost_dev, BUDGET)
@@ -309,15 +325,18 @@ def run_ours(args):
     # dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events on the launch stream)
     bytes_per_img = P * (C * 4 + 4) + NSEG * C * 8
     dur = np.array([a.elapsed_time(b) for a, b in ev_pairs])            # scoring phase of each timed step, ms
+    n_launch = int(launches_seen[0])
     bytes_per_launch = bytes_per_img * n_loc / n_launch
     launch_ms = float(np.mean(dur)) / n_launch
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
     peak, peak_src = peaks()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": scorer_traffic(), "kernel": "bvsb_stats_tma_kernel<19,f32,prob>",
+                "traffic": scorer_traffic() if args.workload == "cityscapes" else None, "kernel": f"bvsb_stats_tma_kernel<{C},f32,prob>",
                 "peak_source": peak_src + ", sustained copy (the kernel runs back to back for the whole phase)",
                 "bytes_per_launch": int(bytes_per_launch), "mean_launch_ms": launch_ms, "launches_per_step": n_launch,
-                "lanes": args.lanes,
+                "lanes": args.lanes, "images_per_launch": round(n_loc / n_launch, 2),
+                "grouping": f"add_batch per loader batch of {REF_BATCH}; a launch covers the batches queued until {args.group_mb} MB "
+                            "of logits wait (<= 8 batches)",
                 "how": "span of the scoring phase (CUDA events on the caller's stream, fork -> join) / launches",
                 "kernel_share_of_step": float(dur.mean() / ms_step),
                 "scoring_phase_ms_per_step": [round(float(x), 3) for x in dur]}
@@ -356,7 +375,7 @@ def run_ours(args):
 
         def e2e_step():
             _lib.call("mas_acquisition_host", h_logits.data_ptr(), 0, h_spx.data_ptr(), n_e, C, H, W, NSEG, TEMP, 1, COEFF,
-                      REF_BATCH, 0, -1, 0, REF_BATCH, h_score.ctypes.data, None, None)
+                      REF_BATCH, 0, C - 1 if BAN_IGNORE else -1, 0, REF_BATCH, h_score.ctypes.data, None, None)
             _lib.call("mas_select_topk_host", h_score.ctypes.data, h_pool.ctypes.data, h_rank.ctypes.data, n_e, NSEG, k_e,
                       h_keys.ctypes.data, h_cnt.ctypes.data)
             return selection.cumulative_cut(cost_all[(h_keys[: int(h_cnt[0])] & np.uint64(0xFFFFFFFF)).astype(np.int64)], k_e - 1)
@@ -410,6 +429,10 @@ def run_ours(args):
 
 def main():
     args = parse()
+    if args.workload == "voc":
+        use_voc_workload()
+    if args.images_per_gpu <= 0:
+        args.images_per_gpu = (POOL_IMAGES + 7) // 8
     if args.impl == "reference":
         run_reference(args)
     else:

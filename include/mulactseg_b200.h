@@ -80,6 +80,18 @@ int mas_bvsb_segment_stats_dev(const void* logits, int logits_dtype, int64_t ima
                                float* cls_sum, int32_t* cls_cnt, double* prob_sum,
                                void* stream);
 
+/* mas_bvsb_segment_stats_multi_dev -- the same pass over up to MAS_MAX_SEGMENTS batches that live in different
+ * allocations (consecutive DataLoader batches) in ONE launch: segment g holds n_img_per_segment[g] images at logits[g]
+ * / ids[g] (image stride image_strides[g], 0 = dense; image_strides may be NULL), and the segments fill consecutive image
+ * rows of cls_sum / cls_cnt / prob_sum (sum of n_img_per_segment rows).  Small batches (VOC-sized images) are
+ * launch-latency-bound one by one; grouped they stream like one big batch.
+ */
+#define MAS_MAX_SEGMENTS 8
+int mas_bvsb_segment_stats_multi_dev(int n_segments, const void* const* logits, int logits_dtype, const int64_t* image_strides,
+                                     const int32_t* const* ids, const int* n_img_per_segment, int channels, int height,
+                                     int width, int nseg, float temperature, float* cls_sum, int32_t* cls_cnt,
+                                     double* prob_sum, void* stream);
+
 /* mas_class_weights_dev -- w_c = (coeff * pbar_c + 1)^-2, pbar = the reference's `cumulated_pred_prob / len(loader)`
  * (active_selection/my_bvsb_predclsbal_pwr.py:33-47): per reference batch of `ref_batch` images (the last may be short)
  * the mean probability of class c = sum of prob_sum rows / (images * pixels_per_image), accumulated over the batches in

@@ -19,7 +19,9 @@ MAS_I32, MAS_I64, MAS_U8 = 0, 1, 2
 MAS_MIOU_BY_TARGET, MAS_MIOU_BY_OUTPUT = 0, 1
 MAS_GROUP_ALL, MAS_GROUP_ONLYMULTI = 0, 1
 MAS_LOSS_CHOICE, MAS_LOSS_GROUP, MAS_LOSS_EXACT_SOFTMAX = 1, 2, 4
+MAS_MAX_CLASSES = 32
 MAS_MAX_LOSS_CLASSES = 31
+MAS_MAX_SEGMENTS = 8
 MAS_THRESHOLD_MEDIAN, MAS_THRESHOLD_MIN = 0, 1
 
 # name -> (restype, argtypes); mirrors include/mulactseg_b200.h one to one
@@ -31,6 +33,8 @@ SIGNATURES = {
                                            c_void_p, c_void_p, c_void_p, c_void_p]),
     "mas_class_weights_dev": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int, c_float, c_void_p, c_void_p]),
     "mas_prefix_cut_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "mas_bvsb_segment_stats_multi_dev": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                                 c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mas_region_scores_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mas_minmax_nonzero_dev": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "mas_dominant_hist_dev": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),

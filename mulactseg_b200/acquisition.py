@@ -14,6 +14,7 @@ from typing import Optional
 
 import torch
 
+from . import _lib
 from . import dist as mdist
 from . import ops
 
@@ -44,17 +45,24 @@ class RegionStats:
     cls_cnt (n,S,C) i32 : pixel count = arg-max histogram (exact)
     prob_sum (n,C)  f64 : sum over pixels of softmax(l/T)   (only when ``need_prob``)
 
-    Consecutive ``add_batch`` launches touch disjoint table rows and only add, so they carry no mutual
-    dependency: with ``lanes`` > 1 they alternate over that many side streams (forked from / joined to the
-    caller's stream with events).  The scorer is a single-wave grid holding a whole SM per CTA, so the CTAs of
-    launch i+1 move onto SMs as the CTAs of launch i retire -- ramp and tail of the ~100 us launches overlap
-    instead of adding a launch gap each.  ``lanes`` = 1 keeps everything on the caller's stream.
+    Consecutive ``add_batch`` calls touch disjoint table rows and only add, so they carry no mutual dependency:
+    * launches alternate over ``lanes`` side streams (forked from / joined to the caller's stream with events).  The scorer
+      is a single-wave grid, so the CTAs of launch i+1 move onto SMs as the CTAs of launch i retire -- ramp and tail of the
+      ~100 us launches overlap instead of adding a launch gap each.  ``lanes`` = 1 keeps everything on the caller's stream.
+    * batches are GROUPED: ``add_batch`` only queues the batch (holding its tensors); a launch covers up to
+      ``MAS_MAX_SEGMENTS`` queued batches and goes out once ``group_bytes`` of logits are waiting (or at ``join``).  One
+      launch per loader batch is launch-latency-bound for small images (VOC: 66 MB per batch of 4) and leaves ramp / tail
+      on the table for big ones; grouped, every launch streams ~1.5 GB.  ``group_bytes`` = 0 launches every batch at once.
     """
 
-    def __init__(self, n_img: int, nseg: int, channels: int, device, need_prob: bool, lanes: int = 2):
+    def __init__(self, n_img: int, nseg: int, channels: int, device, need_prob: bool, lanes: int = 2,
+                 group_bytes: int = 1536 << 20):
         self.n_img, self.nseg, self.channels = int(n_img), int(nseg), int(channels)
         self.lanes = [torch.cuda.Stream(device=device) for _ in range(lanes)] if lanes > 1 else []
+        self.group_bytes = int(group_bytes)
         self._turn, self._dirty = 0, False
+        self._queue, self._queued_bytes, self._queue_first, self._queue_temp, self._queue_n = [], 0, 0, None, 0
+        self.launches = 0
         self._cls_sum = torch.zeros((n_img, nseg, channels), dtype=torch.float32, device=device)
         self._cls_cnt = torch.zeros((n_img, nseg, channels), dtype=torch.int32, device=device)
         self._prob_sum = torch.zeros((n_img, channels), dtype=torch.float64, device=device) if need_prob else None
@@ -77,7 +85,8 @@ class RegionStats:
         return self._prob_sum
 
     def join(self):
-        """Make the caller's current stream wait for every outstanding ``add_batch`` launch."""
+        """Launch what is still queued and make the caller's current stream wait for every outstanding launch."""
+        self.flush()
         if self._dirty:
             main = torch.cuda.current_stream(self._cls_sum.device)
             for lane in self.lanes:
@@ -91,32 +100,69 @@ class RegionStats:
         if self._prob_sum is not None:
             self._prob_sum.zero_()
 
-    def add_batch(self, first_img: int, logits: torch.Tensor, spx: torch.Tensor, temperature: float) -> None:
-        """Fold images [first_img, first_img + B) into the tables (asynchronous)."""
-        b = logits.shape[0]
-        if first_img < 0 or first_img + b > self.n_img:
-            raise RuntimeError(f"batch [{first_img},{first_img + b}) outside the shard of {self.n_img} images")
-        if logits.shape[1] != self.channels:
-            raise RuntimeError(f"expected {self.channels} channels, got {logits.shape[1]}")
-        if not logits.is_cuda or not spx.is_cuda:
-            raise RuntimeError("add_batch: expected CUDA tensors (there is no CPU path)")
-        if spx.dtype != torch.int32:
-            spx = spx.to(torch.int32)
-        self.pixels_per_image = logits.shape[2] * logits.shape[3]
-        spx = spx.contiguous()
-        tables = (self._cls_sum[first_img:first_img + b], self._cls_cnt[first_img:first_img + b],
-                  None if self._prob_sum is None else self._prob_sum[first_img:first_img + b])
+    def flush(self):
+        """One launch over the queued batches (consecutive image rows of the tables)."""
+        if not self._queue:
+            return
+        queue, first, temperature, n = self._queue, self._queue_first, self._queue_temp, self._queue_n
+        self._queue, self._queued_bytes, self._queue_n = [], 0, 0
+        tables = (self._cls_sum[first:first + n], self._cls_cnt[first:first + n],
+                  None if self._prob_sum is None else self._prob_sum[first:first + n])
+        self.launches += 1
         if not self.lanes:
-            ops.bvsb_segment_stats(logits, spx, self.nseg, temperature, *tables)
+            ops.bvsb_segment_stats_multi(queue, self.nseg, temperature, *tables)
             return
         lane = self.lanes[self._turn % len(self.lanes)]
         self._turn += 1
-        lane.wait_stream(torch.cuda.current_stream(logits.device))   # inputs (and the zeroed tables) are ready
-        with torch.cuda.stream(lane):
-            ops.bvsb_segment_stats(logits, spx, self.nseg, temperature, *tables)
-        logits.record_stream(lane)    # the caching allocator must not recycle them before the lane is done
-        spx.record_stream(lane)
+        lane.wait_stream(torch.cuda.current_stream(self._cls_sum.device))   # inputs (and the zeroed tables) are ready
+        ops.bvsb_segment_stats_multi(queue, self.nseg, temperature, *tables, stream=lane.cuda_stream)
+        for x, ids in queue:
+            x.record_stream(lane)     # the caching allocator must not recycle them before the lane is done
+            ids.record_stream(lane)
         self._dirty = True
+
+    def add_batch(self, first_img: int, logits: torch.Tensor, spx: torch.Tensor, temperature: float) -> None:
+        """Fold images [first_img, first_img + B) into the tables (asynchronous; the launch may be deferred until enough
+        batches are queued -- ``join`` / ``finalize`` / reading a table flushes)."""
+        shape = logits.shape
+        b = shape[0]
+        if first_img < 0 or first_img + b > self.n_img:
+            raise RuntimeError(f"batch [{first_img},{first_img + b}) outside the shard of {self.n_img} images")
+        if shape[1] != self.channels:
+            raise RuntimeError(f"expected {self.channels} channels, got {shape[1]}")
+        if not logits.is_cuda or not spx.is_cuda:
+            raise RuntimeError("add_batch: expected CUDA tensors (there is no CPU path)")
+        if not temperature > 0.0:
+            raise RuntimeError("add_batch: temperature must be > 0")
+        # the launch may be deferred: everything the kernel entry would reject is rejected here, at the call that caused it
+        if not 2 <= shape[1] <= _lib.MAS_MAX_CLASSES:
+            raise RuntimeError(f"add_batch: channels={shape[1]} outside [2,{_lib.MAS_MAX_CLASSES}]")
+        if logits.dim() != 4 or logits.dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError(f"logits: expected (B,C,H,W) float32/bfloat16, got {tuple(shape)} {logits.dtype}")
+        if tuple(spx.shape) != (b, shape[2], shape[3]):
+            raise RuntimeError(f"spx shape {tuple(spx.shape)} does not match logits {tuple(shape)}")
+        if b * shape[1] > 0 and (logits.stride(3) != 1 or logits.stride(2) != shape[3] or logits.stride(1) != shape[2] * shape[3]
+                                 or (b > 1 and logits.stride(0) < shape[1] * shape[2] * shape[3])):
+            raise RuntimeError("logits: expected NCHW layout with contiguous planes")
+        if spx.dtype != torch.int32:
+            spx = spx.to(torch.int32)
+        if not spx.is_contiguous():
+            spx = spx.contiguous()
+        self.pixels_per_image = shape[2] * shape[3]
+        queue = self._queue
+        if queue:
+            head = queue[0][0]
+            if first_img != self._queue_first + self._queue_n or temperature != self._queue_temp \
+                    or head.shape[1:] != shape[1:] or head.dtype != logits.dtype:
+                self.flush()
+                queue = self._queue
+        if not queue:
+            self._queue_first, self._queue_temp = first_img, temperature
+        queue.append((logits, spx))
+        self._queue_n += b
+        self._queued_bytes += logits.numel() * logits.element_size()
+        if self._queued_bytes >= self.group_bytes or len(queue) >= _lib.MAS_MAX_SEGMENTS:
+            self.flush()
 
 
 def predicted_class_weights(prob_sum_all: torch.Tensor, pixels_per_image: int, ref_batch: int, coeff: float) -> torch.Tensor:

@@ -40,10 +40,16 @@ constexpr int kLdgThreads = 128;
 constexpr int kTmaMaxWarps = 8;
 constexpr int kTmaStripPx = 128;  // pixels per strip row on the TMA path (32 lanes x 4)
 
+// A launch covers up to kMaxSeg SEGMENTS: batches of images that live in different allocations (consecutive loader
+// batches) but fill consecutive rows of the tables.  Images are numbered 0 .. n_img-1 across the segments.
+constexpr int kMaxSeg = MAS_MAX_SEGMENTS;
+
 struct StatsParams {
-    const void* logits;
-    const int32_t* ids;
-    long long image_stride;  // elements between images of `logits`
+    const void* seg_logits[kMaxSeg];
+    const int32_t* seg_ids[kMaxSeg];
+    long long seg_stride[kMaxSeg];   // elements between images of the segment's logits
+    int seg_first[kMaxSeg + 1];      // first image of segment g; seg_first[n_seg] = n_img
+    int n_seg;
     int n_img, C, H, W, S;
     float scale;             // log2(e) / T
     int strips;              // column strips per image
@@ -53,6 +59,12 @@ struct StatsParams {
     int32_t* cls_cnt;
     double* prob_sum;
 };
+
+__device__ __forceinline__ int seg_of(const StatsParams& p, int img) {
+    int g = 0;
+    while (g + 1 < p.n_seg && img >= p.seg_first[g + 1]) ++g;
+    return g;
+}
 
 // ------------------------------------------------------------------------------------------ loads
 template <typename T, int VEC>
@@ -245,8 +257,15 @@ __global__ void __launch_bounds__(kLdgThreads) bvsb_stats_ldg_kernel(const Stats
     at.seek(r0, p.strips, p.H);
 
     const size_t P = (size_t)p.H * p.W;
-    const T* img_logits = reinterpret_cast<const T*>(p.logits) + (size_t)at.img * (size_t)p.image_stride;
-    const int32_t* img_ids = p.ids + (size_t)at.img * P;
+    const T* img_logits;
+    const int32_t* img_ids;
+    auto locate = [&](int img) {      // pointers of image `img` inside its segment
+        const int g = seg_of(p, img);
+        const size_t local = (size_t)(img - p.seg_first[g]);
+        img_logits = reinterpret_cast<const T*>(p.seg_logits[g]) + local * (size_t)p.seg_stride[g];
+        img_ids = p.seg_ids[g] + local * P;
+    };
+    locate(at.img);
     w.img_region = (long long)at.img * p.S;
     int x0 = (at.strip * 32 + lane) * VEC;
 
@@ -280,8 +299,7 @@ __global__ void __launch_bounds__(kLdgThreads) bvsb_stats_ldg_kernel(const Stats
             if (step == 2) {
                 w.flush();
                 w.flush_prob(p.prob_sum, img_done, lane);
-                img_logits += (size_t)p.image_stride;
-                img_ids += P;
+                if (at.img < p.n_img) locate(at.img);
                 w.img_region += p.S;
             }
         }
@@ -330,10 +348,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
 //   [warps][stages] stage = { T logits[C][128] ; int32 ids[128] }     filled by TMA
 //   [C][threads] uint2                                                private accumulation columns
 //   [warps][stages] uint64                                            mbarriers ("stage full")
+struct TmaMaps {     // one pair of tensor maps per segment
+    CUtensorMap logits[kMaxSeg];
+    CUtensorMap ids[kMaxSeg];
+};
+
 template <int CMAX, bool EXACT, bool NEED_PROB, typename T>
 __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1)
-bvsb_stats_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const __grid_constant__ CUtensorMap tm_ids,
-                      const StatsParams p) {
+bvsb_stats_tma_kernel(const __grid_constant__ TmaMaps maps, const StatsParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // TMA destinations: 128-byte aligned
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -367,13 +389,15 @@ bvsb_stats_tma_kernel(const __grid_constant__ CUtensorMap tm_logits, const __gri
     at.seek(r0, p.strips, p.H);
     ahead = at;
     long long issued = r0;
+    int ahead_seg = seg_of(p, ahead.img);       // segment of the image being issued (lane 0 only uses it)
     auto issue = [&](int s) {  // lane 0 only
         const uint32_t bar = smem_u32(bars + s);
         const uint32_t dst = smem_u32(my_stages + (size_t)s * stage_bytes);
+        const int local = ahead.img - p.seg_first[ahead_seg];
         mbar_expect_tx(bar, stage_bytes);
-        tma_load_4d(dst, &tm_logits, bar, ahead.strip * kTmaStripPx, ahead.y, 0, ahead.img, policy);
-        tma_load_3d(dst + (uint32_t)C * plane_bytes, &tm_ids, bar, ahead.strip * kTmaStripPx, ahead.y, ahead.img, policy);
-        ahead.advance(p.strips, p.H);
+        tma_load_4d(dst, &maps.logits[ahead_seg], bar, ahead.strip * kTmaStripPx, ahead.y, 0, local, policy);
+        tma_load_3d(dst + (uint32_t)C * plane_bytes, &maps.ids[ahead_seg], bar, ahead.strip * kTmaStripPx, ahead.y, local, policy);
+        if (ahead.advance(p.strips, p.H) == 2 && ahead_seg + 1 < p.n_seg && ahead.img >= p.seg_first[ahead_seg + 1]) ++ahead_seg;
         ++issued;
     };
     if (lane == 0) {
@@ -512,28 +536,32 @@ cudaError_t launch_tma(StatsParams p, cudaStream_t stream, bool* unsupported) {
     p.total_rows = (long long)p.n_img * p.strips * p.H;
     p.stages = stages;
 
-    CUtensorMap tm_logits, tm_ids;
-    {
-        const cuuint64_t dims[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.C, (cuuint64_t)p.n_img};
-        const cuuint64_t strides[3] = {(cuuint64_t)p.W * elt, (cuuint64_t)p.H * p.W * elt, (cuuint64_t)p.image_stride * elt};
-        const cuuint32_t box[4] = {kTmaStripPx, 1, (cuuint32_t)p.C, 1};
-        const cuuint32_t estr[4] = {1, 1, 1, 1};
-        if (encode(&tm_logits, elt == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
-                   const_cast<void*>(p.logits), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return cudaSuccess;
+    TmaMaps maps;
+    for (int g = 0; g < p.n_seg; ++g) {
+        const cuuint64_t n_seg_img = (cuuint64_t)(p.seg_first[g + 1] - p.seg_first[g]);
+        {
+            const cuuint64_t dims[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.C, n_seg_img};
+            const cuuint64_t strides[3] = {(cuuint64_t)p.W * elt, (cuuint64_t)p.H * p.W * elt, (cuuint64_t)p.seg_stride[g] * elt};
+            const cuuint32_t box[4] = {kTmaStripPx, 1, (cuuint32_t)p.C, 1};
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            if (encode(&maps.logits[g], elt == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                       const_cast<void*>(p.seg_logits[g]), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return cudaSuccess;
+        }
+        {
+            const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, n_seg_img};
+            const cuuint64_t strides[2] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.H * p.W * 4};
+            const cuuint32_t box[3] = {kTmaStripPx, 1, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            if (encode(&maps.ids[g], CU_TENSOR_MAP_DATA_TYPE_INT32, 3, const_cast<int32_t*>(p.seg_ids[g]), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return cudaSuccess;
+        }
     }
-    {
-        const cuuint64_t dims[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.n_img};
-        const cuuint64_t strides[2] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.H * p.W * 4};
-        const cuuint32_t box[3] = {kTmaStripPx, 1, 1};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        if (encode(&tm_ids, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, const_cast<int32_t*>(p.ids), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return cudaSuccess;
-    }
+    for (int g = p.n_seg; g < kMaxSeg; ++g) { maps.logits[g] = maps.logits[0]; maps.ids[g] = maps.ids[0]; }
     *unsupported = false;
 
     auto kernel = bvsb_stats_tma_kernel<CMAX, EXACT, NEED_PROB, T>;
@@ -553,7 +581,7 @@ cudaError_t launch_tma(StatsParams p, cudaStream_t stream, bool* unsupported) {
     }
     const long long cap = (p.total_rows + 8 * warps - 1) / (8 * warps);
     const long long blocks = std::max<long long>(1, std::min<long long>((long long)mas::sm_count() * per_sm, cap));
-    kernel<<<(unsigned)blocks, warps * 32, smem, stream>>>(tm_logits, tm_ids, p);
+    kernel<<<(unsigned)blocks, warps * 32, smem, stream>>>(maps, p);
     mas::count_launches(1);
     return cudaGetLastError();
 }
@@ -589,36 +617,52 @@ cudaError_t dispatch_channels(const StatsParams& p, int path, cudaStream_t strea
 
 }  // namespace
 
-extern "C" int mas_bvsb_segment_stats_dev(const void* logits, int logits_dtype, int64_t image_stride, const int32_t* ids,
-                                          int n_img, int channels, int height, int width, int nseg,
-                                          float temperature, float* cls_sum, int32_t* cls_cnt, double* prob_sum,
-                                          void* stream) {
-    MAS_REQUIRE(logits && ids && cls_sum && cls_cnt, MAS_E_BADARG, "bvsb_segment_stats: null pointer");
-    MAS_REQUIRE(n_img >= 0 && height > 0 && width > 0 && nseg > 0, MAS_E_BADARG, "bvsb_segment_stats: bad shape");
+extern "C" int mas_bvsb_segment_stats_multi_dev(int n_segments, const void* const* logits, int logits_dtype,
+                                                const int64_t* image_strides, const int32_t* const* ids, const int* n_img_per_segment,
+                                                int channels, int height, int width, int nseg, float temperature,
+                                                float* cls_sum, int32_t* cls_cnt, double* prob_sum, void* stream) {
+    MAS_REQUIRE(logits && ids && n_img_per_segment && cls_sum && cls_cnt, MAS_E_BADARG, "bvsb_segment_stats: null pointer");
+    MAS_REQUIRE(n_segments >= 0 && n_segments <= kMaxSeg, MAS_E_RANGE, "bvsb_segment_stats: n_segments=%d outside [0,%d]", n_segments, kMaxSeg);
+    MAS_REQUIRE(height > 0 && width > 0 && nseg > 0, MAS_E_BADARG, "bvsb_segment_stats: bad shape");
     MAS_REQUIRE(channels >= 2 && channels <= MAS_MAX_CLASSES, MAS_E_RANGE,
                 "bvsb_segment_stats: channels=%d outside [2,%d]", channels, MAS_MAX_CLASSES);
     MAS_REQUIRE(temperature > 0.f, MAS_E_BADARG, "bvsb_segment_stats: temperature must be > 0");
     MAS_REQUIRE(logits_dtype == MAS_F32 || logits_dtype == MAS_BF16, MAS_E_BADARG, "bvsb_segment_stats: bad dtype");
-    if (n_img == 0) return 0;
     const long long plane = (long long)height * width;
-    if (image_stride == 0) image_stride = (long long)channels * plane;
-    MAS_REQUIRE(image_stride >= (long long)channels * plane, MAS_E_BADARG, "bvsb_segment_stats: image_stride too small");
-    MAS_REQUIRE((long long)n_img * ((width + 31) / 32) * height < (1ll << 40), MAS_E_RANGE, "bvsb_segment_stats: too many rows");
-
     const size_t elt = logits_dtype == MAS_F32 ? 4 : 2;
+
+    StatsParams p;
+    p.n_seg = 0; p.n_img = 0;
+    p.seg_first[0] = 0;
     // 128-bit (f32) / 64-bit (bf16) row segments need every plane row to start VEC-aligned;
-    // TMA additionally needs 16-byte global strides and base addresses
-    const bool vec4 = (width % 4 == 0) && (image_stride % 4 == 0) && (((uintptr_t)logits) % (4 * elt) == 0) &&
-                      (((uintptr_t)ids) % 16 == 0);
-    const bool tma_ok = vec4 && ((width * elt) % 16 == 0) && ((image_stride * elt) % 16 == 0) &&
-                        (((uintptr_t)logits) % 16 == 0);
+    // TMA additionally needs 16-byte global strides and base addresses -- for EVERY segment of the launch
+    bool vec4 = (width % 4 == 0), tma_ok = ((width * elt) % 16 == 0);
+    for (int g = 0; g < n_segments; ++g) {
+        MAS_REQUIRE(n_img_per_segment[g] >= 0, MAS_E_BADARG, "bvsb_segment_stats: negative image count");
+        if (n_img_per_segment[g] == 0) continue;
+        MAS_REQUIRE(logits[g] && ids[g], MAS_E_BADARG, "bvsb_segment_stats: null segment pointer");
+        long long stride = image_strides ? image_strides[g] : 0;
+        if (stride == 0) stride = (long long)channels * plane;
+        MAS_REQUIRE(stride >= (long long)channels * plane, MAS_E_BADARG, "bvsb_segment_stats: image_stride too small");
+        const int k = p.n_seg++;
+        p.seg_logits[k] = logits[g]; p.seg_ids[k] = ids[g]; p.seg_stride[k] = stride;
+        p.n_img += n_img_per_segment[g];
+        p.seg_first[k + 1] = p.n_img;
+        vec4 = vec4 && (stride % 4 == 0) && (((uintptr_t)logits[g]) % (4 * elt) == 0) && (((uintptr_t)ids[g]) % 16 == 0);
+        tma_ok = tma_ok && ((stride * elt) % 16 == 0) && (((uintptr_t)logits[g]) % 16 == 0);
+    }
+    if (p.n_img == 0) return 0;
+    for (int g = p.n_seg; g < kMaxSeg; ++g) {
+        p.seg_logits[g] = p.seg_logits[0]; p.seg_ids[g] = p.seg_ids[0]; p.seg_stride[g] = p.seg_stride[0];
+        p.seg_first[g + 1] = p.n_img;
+    }
+    MAS_REQUIRE((long long)p.n_img * ((width + 31) / 32) * height < (1ll << 40), MAS_E_RANGE, "bvsb_segment_stats: too many rows");
+    tma_ok = tma_ok && vec4;
     int path = tma_ok ? kPathTma : (vec4 ? kPathLdg4 : kPathLdg1);
     const char* forced = getenv("MAS_SCORER_PATH");   // development switch: "ldg" keeps the register path
     if (forced && forced[0] == 'l' && path == kPathTma) path = kPathLdg4;
 
-    StatsParams p;
-    p.logits = logits; p.ids = ids; p.image_stride = image_stride;
-    p.n_img = n_img; p.C = channels; p.H = height; p.W = width; p.S = nseg;
+    p.C = channels; p.H = height; p.W = width; p.S = nseg;
     p.scale = 1.4426950408889634f / temperature;
     p.strips = 0; p.total_rows = 0; p.stages = 0;
     p.cls_sum = cls_sum; p.cls_cnt = cls_cnt; p.prob_sum = prob_sum;
@@ -631,4 +675,14 @@ extern "C" int mas_bvsb_segment_stats_dev(const void* logits, int logits_dtype, 
         e = prob_sum ? dispatch_channels<true, __nv_bfloat16>(p, path, st) : dispatch_channels<false, __nv_bfloat16>(p, path, st);
     if (e != cudaSuccess) return mas::cuda_fail(e, "bvsb_stats kernel launch");
     return 0;
+}
+
+extern "C" int mas_bvsb_segment_stats_dev(const void* logits, int logits_dtype, int64_t image_stride, const int32_t* ids,
+                                          int n_img, int channels, int height, int width, int nseg,
+                                          float temperature, float* cls_sum, int32_t* cls_cnt, double* prob_sum,
+                                          void* stream) {
+    MAS_REQUIRE(logits && ids && cls_sum && cls_cnt, MAS_E_BADARG, "bvsb_segment_stats: null pointer");
+    MAS_REQUIRE(n_img >= 0, MAS_E_BADARG, "bvsb_segment_stats: bad shape");
+    return mas_bvsb_segment_stats_multi_dev(1, &logits, logits_dtype, &image_stride, &ids, &n_img, channels, height, width, nseg,
+                                            temperature, cls_sum, cls_cnt, prob_sum, stream);
 }

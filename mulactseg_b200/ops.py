@@ -88,6 +88,53 @@ def bvsb_segment_stats(logits: torch.Tensor, spx: torch.Tensor, nseg: int, tempe
                   _ptr(prob_sum), _stream(logits))
 
 
+def bvsb_segment_stats_multi(batches, nseg: int, temperature: float, cls_sum: torch.Tensor, cls_cnt: torch.Tensor,
+                             prob_sum: Optional[torch.Tensor], stream: Optional[int] = None) -> None:
+    """``bvsb_segment_stats`` over several (logits, spx) batches in ONE launch (``mas_bvsb_segment_stats_multi_dev``):
+    the batches live in different allocations but fill consecutive image rows of the tables.  All batches share
+    dtype, C, H, W.  ``stream``: raw CUDA stream handle (default: torch's current stream)."""
+    import ctypes
+    if not batches:
+        return
+    if len(batches) > _lib.MAS_MAX_SEGMENTS:
+        raise RuntimeError(f"at most {_lib.MAS_MAX_SEGMENTS} batches per launch")
+    first = batches[0][0]
+    if not isinstance(first, torch.Tensor) or not first.is_cuda:
+        raise RuntimeError("logits: expected a CUDA tensor (there is no CPU path)")
+    _, c, h, w = first.shape
+    ptrs, strides, ids, counts, total = [], [], [], [], 0
+    for logits, spx in batches:
+        if logits.dim() != 4 or logits.dtype != first.dtype or logits.dtype not in (torch.float32, torch.bfloat16) \
+                or tuple(logits.shape[1:]) != (c, h, w) or logits.device != first.device:
+            raise RuntimeError("logits: every batch must be (B,C,H,W) float32/bfloat16 with the same C, H, W, dtype and device")
+        _want(spx, "spx", torch.int32, 3)
+        b = logits.shape[0]
+        if b * c * h * w > 0 and (logits.stride(3) != 1 or logits.stride(2) != w or logits.stride(1) != h * w
+                                  or (b > 1 and logits.stride(0) < c * h * w)):
+            raise RuntimeError("logits: expected NCHW layout with contiguous planes")
+        if tuple(spx.shape) != (b, h, w):
+            raise RuntimeError(f"spx shape {tuple(spx.shape)} does not match logits {tuple(logits.shape)}")
+        ptrs.append(logits.data_ptr()); ids.append(spx.data_ptr()); counts.append(b)
+        strides.append(logits.stride(0) if b > 1 else c * h * w)
+        total += b
+    _want(cls_sum, "cls_sum", torch.float32)
+    _want(cls_cnt, "cls_cnt", torch.int32)
+    if cls_sum.numel() != total * nseg * c or cls_cnt.numel() != total * nseg * c:
+        raise RuntimeError("cls_sum / cls_cnt must hold (sum of B)*nseg*C elements")
+    if prob_sum is not None:
+        _want(prob_sum, "prob_sum", torch.float64)
+        if prob_sum.numel() != total * c:
+            raise RuntimeError("prob_sum must hold (sum of B)*C elements")
+    if total == 0:
+        return
+    n = len(batches)
+    with _on(first):
+        _lib.call("mas_bvsb_segment_stats_multi_dev", n, (ctypes.c_void_p * n)(*ptrs),
+                  _lib.MAS_F32 if first.dtype == torch.float32 else _lib.MAS_BF16, (ctypes.c_int64 * n)(*strides),
+                  (ctypes.c_void_p * n)(*ids), (ctypes.c_int * n)(*counts), c, h, w, int(nseg), float(temperature),
+                  cls_sum.data_ptr(), cls_cnt.data_ptr(), _ptr(prob_sum), _stream(first) if stream is None else int(stream))
+
+
 def class_weights(prob_sum: torch.Tensor, pixels_per_image: int, ref_batch: int, coeff: float) -> torch.Tensor:
     """(N,C) f64 per-image probability sums in pool order -> (C,) f32 class weights (``mas_class_weights_dev``)."""
     _want(prob_sum, "prob_sum", torch.float64, 2)

@@ -159,6 +159,42 @@ def test_voc_size_properties(shape):
     assert float(score[dominant == c - 1].abs().max() if (dominant == c - 1).any() else 0.0) == 0.0
 
 
+@pytest.mark.parametrize("path", ["tma", "ldg"])
+@pytest.mark.parametrize("shape", [(11, 19, 24, 128, 40, 1), (21, 22, 37, 132, 150, 2), (8, 6, 9, 33, 7, 3)])
+def test_grouped_launches_equal_single_launches(shape, path, monkeypatch):
+    """Several loader batches (separate allocations, short last batch, more batches than one launch takes) folded by
+    grouped launches == one launch per batch: identical histograms, sums equal up to the order of the fp32 atomics."""
+    from mulactseg_b200 import acquisition as acq
+    monkeypatch.setenv("MAS_SCORER_PATH", path)
+    n, c, h, w, nseg, bs = shape
+    logits = synth.logits(n, c, h, w, "cosine", seed=n)
+    spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=n + 1, dtype=torch.int32)
+    parts = [(logits[i:i + bs].clone().to(DEV), spx[i:i + bs].clone().to(DEV)) for i in range(0, n, bs)]   # own allocations
+    one = acq.RegionStats(n, nseg, c, DEV, need_prob=True, group_bytes=0)
+    grouped = acq.RegionStats(n, nseg, c, DEV, need_prob=True, group_bytes=1 << 40)
+    first = 0
+    for x, ids in parts:
+        one.add_batch(first, x, ids, 0.1)
+        grouped.add_batch(first, x, ids, 0.1)
+        first += x.shape[0]
+    assert one.launches == len(parts) and grouped.launches == len(parts) // 8   # only full groups of 8 went out so far ...
+    assert torch.equal(one.cls_cnt, grouped.cls_cnt)                     # ... reading a table flushes the rest
+    assert grouped.launches == -(-len(parts) // 8)
+    np.testing.assert_allclose(grouped.cls_sum.cpu().numpy(), one.cls_sum.cpu().numpy(), rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(grouped.prob_sum.cpu().numpy(), one.prob_sum.cpu().numpy(), rtol=1e-6)   # fp32 per-thread partials
+    # a gap in the image rows or another temperature starts a new launch instead of corrupting the group
+    odd = acq.RegionStats(n, nseg, c, DEV, need_prob=False, group_bytes=1 << 40)
+    odd.add_batch(0, parts[0][0], parts[0][1], 0.1)
+    odd.add_batch(2 * bs, parts[2][0], parts[2][1], 0.1)
+    odd.add_batch(bs, parts[1][0], parts[1][1], 0.5)
+    assert odd.launches == 2
+    ref = acq.RegionStats(n, nseg, c, DEV, need_prob=False, group_bytes=0)
+    ref.add_batch(0, parts[0][0], parts[0][1], 0.1)
+    ref.add_batch(2 * bs, parts[2][0], parts[2][1], 0.1)
+    ref.add_batch(bs, parts[1][0], parts[1][1], 0.5)
+    assert torch.equal(odd.cls_cnt, ref.cls_cnt)
+
+
 def test_ids_outside_range_are_ignored_and_empty_batch():
     from mulactseg_b200 import acquisition as acq
     n, c, h, w, nseg = 1, 6, 16, 32, 5

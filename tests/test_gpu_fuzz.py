@@ -86,7 +86,7 @@ def test_losses_random_shapes(seed):
     ce_ref, mc_ref = (torch.as_tensor(v, dtype=torch.float32) for v in olo.onehot_ce_multihot_choice(xr, trg, spx, mask, temp, True))
     total_ref = 16.0 * ce_ref + 8.0 * mc_ref + g_ref
     msg = f"seed {seed}: n={n} c={c} {h}x{w} nseg={nseg} rho={rho} T={temp}"
-    np.testing.assert_allclose([ce.item(), mc.item(), g.item()], [float(ce_ref.detach()), float(mc_ref.detach()), float(g_ref.detach())], rtol=1e-5, atol=1.2e-7, err_msg=msg)
+    np.testing.assert_allclose([ce.item(), mc.item(), g.item()], [float(torch.as_tensor(v).detach()) for v in (ce_ref, mc_ref, g_ref)], rtol=1e-5, atol=1.2e-7, err_msg=msg)
     if total_ref.requires_grad:
         total_ref.backward()
         ref_grad = xr.grad.numpy()

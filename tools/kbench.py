@@ -47,7 +47,7 @@ def main():
         logits = synth.logits(pool, c, h, w, "cosine", seed=1, device=dev)
         spx = synth.superpixel_map(pool, h, w, s, "jitter", seed=2, device=dev, dtype=torch.int32)
         for need_prob in (True, False):
-            stats = acq.RegionStats(pool, s, c, dev, need_prob)
+            stats = acq.RegionStats(pool, s, c, dev, need_prob, group_bytes=0)
             for i in range(6):
                 j = (i % 6) * 4
                 stats.add_batch(j, logits[j:j + 4], spx[j:j + 4], 0.1)
@@ -73,7 +73,7 @@ def main():
                             for k in ("MAS_SCORER_PATH", "MAS_SCORER_STAGES", "MAS_SCORER_WARPS"):
                                 os.environ.pop(k, None)
                             os.environ.update({k: v for k, v in env.items() if k != "LANES"})
-                            stats = acq.RegionStats(pool, s, c, dev, need_prob, lanes=int(env.get("LANES", 2)))
+                            stats = acq.RegionStats(pool, s, c, dev, need_prob, lanes=int(env.get("LANES", 2)), group_bytes=0)
                             nb = pool // batch
 
                             def run(i, stats=stats, batch=batch, nb=nb):
