@@ -90,22 +90,36 @@ __global__ void finalize_scores_kernel(float* __restrict__ score, const int32_t*
 
 // w_c = (coeff * pbar_c + 1)^-2 with pbar = mean over the reference's batches of the per-batch mean probability:
 // `cumulated += mean(prob, dim=(0,2,3))` per batch in loader order, fp32, then `/ len(loader)`
-// (active_selection/my_bvsb_predclsbal_pwr.py:36-47).  One thread per class walks the batches in that order.
-__global__ void class_weights_kernel(const double* __restrict__ prob_sum, long long n_img, int C, double pixels, int ref_batch,
-                                     float coeff, float* __restrict__ weight) {
-    const int c = threadIdx.x;
-    if (c >= C) return;
+// (active_selection/my_bvsb_predclsbal_pwr.py:36-47).  The per-batch means are computed by the whole CTA, kMeanBatches
+// at a time, into shared memory; one thread per class then adds them in loader order (the reference's fp32 sequence).
+constexpr int kMeanBatches = 256;
+
+__global__ void __launch_bounds__(1024) class_weights_kernel(const double* __restrict__ prob_sum, long long n_img, int C, double pixels,
+                                                             int ref_batch, float coeff, float* __restrict__ weight) {
+    __shared__ float means[kMeanBatches][MAS_MAX_CLASSES];
+    const long long n_batches = (n_img + ref_batch - 1) / ref_batch;
     float cumulated = 0.f;
-    long long n_batches = 0;
-    for (long long b0 = 0; b0 < n_img; b0 += ref_batch, ++n_batches) {
-        const int len = (int)min((long long)ref_batch, n_img - b0);
-        double s = 0.0;
-        for (int i = 0; i < len; ++i) s += prob_sum[(b0 + i) * C + c];
-        cumulated += (float)(s / ((double)len * pixels));
+    for (long long chunk = 0; chunk < n_batches; chunk += kMeanBatches) {
+        const int len_chunk = (int)min((long long)kMeanBatches, n_batches - chunk);
+        for (int idx = threadIdx.x; idx < len_chunk * C; idx += blockDim.x) {
+            const int bi = idx / C, c = idx - bi * C;
+            const long long b0 = (chunk + bi) * ref_batch;
+            const int len = (int)min((long long)ref_batch, n_img - b0);
+            double s = 0.0;
+            for (int i = 0; i < len; ++i) s += prob_sum[(b0 + i) * C + c];
+            means[bi][c] = (float)(s / ((double)len * pixels));
+        }
+        __syncthreads();
+        if (threadIdx.x < C) {
+            for (int bi = 0; bi < len_chunk; ++bi) cumulated += means[bi][threadIdx.x];
+        }
+        __syncthreads();
     }
-    const float pbar = cumulated / (float)n_batches;
-    const float x = coeff * pbar + 1.f;
-    weight[c] = 1.f / (x * x);
+    if (threadIdx.x < C) {
+        const float pbar = cumulated / (float)n_batches;
+        const float x = coeff * pbar + 1.f;
+        weight[threadIdx.x] = 1.f / (x * x);
+    }
 }
 
 }  // namespace
@@ -115,7 +129,7 @@ extern "C" int mas_class_weights_dev(const double* prob_sum, int64_t n_img, int 
     MAS_REQUIRE(prob_sum && weight, MAS_E_BADARG, "class_weights: null pointer");
     MAS_REQUIRE(n_img > 0 && pixels_per_image > 0 && ref_batch > 0, MAS_E_BADARG, "class_weights: bad size");
     MAS_REQUIRE(channels >= 1 && channels <= MAS_MAX_CLASSES, MAS_E_RANGE, "class_weights: channels out of range");
-    class_weights_kernel<<<1, MAS_MAX_CLASSES, 0, (cudaStream_t)stream>>>(prob_sum, n_img, channels, (double)pixels_per_image,
+    class_weights_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(prob_sum, n_img, channels, (double)pixels_per_image,
                                                                          ref_batch, coeff, weight);
     mas::count_launches(1);
     MAS_LAUNCH_OK("class_weights_kernel");

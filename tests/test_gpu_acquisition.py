@@ -195,6 +195,25 @@ def test_grouped_launches_equal_single_launches(shape, path, monkeypatch):
     assert torch.equal(odd.cls_cnt, ref.cls_cnt)
 
 
+@pytest.mark.parametrize("n,c,bs", [(1, 2, 4), (7, 19, 4), (2975, 20, 4), (1031, 22, 3), (300, 32, 1)])
+def test_class_weights_kernel_matches_the_reference_sequence(n, c, bs):
+    """mas_class_weights_dev == `cumulated += batch mean` in loader order in fp32 (my_bvsb_predclsbal_pwr.py:36-47),
+    short last batch and more batches than one shared-memory chunk included."""
+    from mulactseg_b200 import ops
+    g = torch.Generator().manual_seed(n * c)
+    pixels = 1000
+    prob = torch.rand((n, c), generator=g, dtype=torch.float64) * pixels / c
+    cumulated = torch.zeros(c, dtype=torch.float32)
+    n_batches = 0
+    for b0 in range(0, n, bs):
+        part = prob[b0:b0 + bs]
+        cumulated += (part.sum(dim=0) / (part.shape[0] * pixels)).to(torch.float32)
+        n_batches += 1
+    want = (6.0 * (cumulated / n_batches) + 1.0) ** (-2)
+    got = ops.class_weights(prob.to(DEV), pixels, bs, 6.0).cpu()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-6)    # 1 / (x * x) vs torch pow(-2): an ulp or two
+
+
 def test_ids_outside_range_are_ignored_and_empty_batch():
     from mulactseg_b200 import acquisition as acq
     n, c, h, w, nseg = 1, 6, 16, 32, 5
