@@ -78,8 +78,8 @@ def peaks():
 
 def scorer_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the scorer, from the committed ncu --set full capture
-    of the same configuration (4 images x 19 x 1024 x 2048 f32 per launch); None if the summary is missing."""
-    path = os.path.join(ROOT, "profiles", "r1_v5_scorer_tma_c19_full.txt")
+    of the same configuration (12 images x 19 x 1024 x 2048 f32 per grouped launch); None if the summary is missing."""
+    path = os.path.join(ROOT, "profiles", "r1_v7_scorer_tma_c19_12img_full.txt")
     try:
         with open(path) as f:
             vals = [int(line.split()[-1]) for line in f if line.startswith("traffic = dram read + write")]
