@@ -268,6 +268,7 @@ class OnehotCEMultihotChoice(MultiChoiceCE):
         assert self.reduction == "mean"
         self.assert_partition = assert_partition
         self._pending = None        # (pinned host copy of the empty-row count, event) of the previous call
+        self._pinned = None         # the pinned buffer, allocated once
 
     def check_partition(self):
         """Raise if the previous call saw a selected pixel whose superpixel has no candidate class
@@ -285,7 +286,9 @@ class OnehotCEMultihotChoice(MultiChoiceCE):
         if self.strict_multihot:
             return out[ONE_HOT], out[MULTI_STRICT]
         if self.assert_partition == "deferred":
-            host = torch.empty(1, dtype=torch.float64).pin_memory() if self._pending is None else self._pending[0]
+            if self._pinned is None:
+                self._pinned = torch.empty(1, dtype=torch.float64).pin_memory()
+            host = self._pinned
             host.copy_(out[COUNTS][2:3], non_blocking=True)
             event = torch.cuda.Event()
             event.record()
