@@ -89,15 +89,16 @@ def scorer_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 25 ms.  The sampler is started well before the timed region
+    (nvidia-smi takes a moment to come up); ``stop(t0, t1)`` keeps the samples whose timestamps fall inside it."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(index), "-lms", "25"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -105,25 +106,32 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([p.strip() for p in line.split(",")])
+            self.rows.append((time.time(), [p.strip() for p in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0: float, t1: float):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.1)
         self.proc.terminate()
         self.thread.join(timeout=2)
+        import datetime
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for seen, r in self.rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                stamp = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                stamp = seen
+            if not (t0 <= stamp <= t1):
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "interval_ms": 25}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
@@ -300,21 +308,25 @@ def run_ours(args):
         out["score_host_enqueue"] = round(enqueue_ms, 3)
         return out
 
+    sampler = ClockSampler(local) if rank == 0 else None     # comes up while the phase breakdown runs
     phase_ms = phases() if world == 1 else None
+    if sampler is not None:
+        time.sleep(0.3)
     sync_all()
     launches0 = lib.mas_kernel_launches()
-    sampler = ClockSampler(local) if rank == 0 else None
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.cudart().cudaProfilerStart()   # no-op unless run under `ncu --profile-from-start off`
     wall0 = time.perf_counter()
+    clock_t0 = time.time()
     t_start.record()
     for _ in range(args.steps):
         picked = step(True)
     t_end.record()
     sync_all()
     wall = time.perf_counter() - wall0
+    clock_t1 = time.time()
     torch.cuda.cudart().cudaProfilerStop()
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(clock_t0, clock_t1) if sampler else None
     launches = lib.mas_kernel_launches() - launches0
     ms_total = torch.tensor([max(t_start.elapsed_time(t_end), 0.0)], device=dev, dtype=torch.float64)
     if world > 1:
