@@ -217,7 +217,7 @@ def workload_config(args, images_per_gpu, note=""):
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch.distributed as td
-    from mulactseg_b200 import _lib, acquisition as acq, dist as mdist, ops, selection, synth
+    from mulactseg_b200 import _lib, acquisition as acq, selection, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -1,5 +1,4 @@
 """CPU tier: the C-ABI library loads without a GPU and exports every symbol include/mulactseg_b200.h declares."""
-import ctypes
 import os
 import re
 

@@ -1,6 +1,5 @@
 """GPU parity of the acquisition path (kernels called through the C ABI) against the CPU oracle and
 against the vectors produced by the unmodified reference (tests/golden/acquisition.npz)."""
-import ctypes
 import importlib
 import os
 
