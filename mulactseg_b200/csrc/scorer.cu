@@ -217,22 +217,26 @@ struct Walker {
         }
         // ---- then the segmented accumulation
         // does this row still touch the current superpixel?  if not, move on to the row's first id
+        // ids outside [0, S) (crop padding, -1, garbage) become -2: never equal to `cur` (>= -1), never accumulated
+        int sid[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) sid[j] = ((unsigned)id[j] < (unsigned)S) ? id[j] : -2;
         bool touches = false;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) touches |= (id[j] == cur);
+        for (int j = 0; j < VEC; ++j) touches |= (sid[j] == cur);
         if (!touches) {
             flush();
-            cur = ((unsigned)id[0] < (unsigned)S) ? id[0] : -1;
+            cur = sid[0] >= 0 ? sid[0] : -1;
         }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            const int s = id[j];
+            const int s = sid[j];
             if (s == cur) {
                 uint2 slot = col[top1[j] * col_stride];
                 slot.x = __float_as_uint(__uint_as_float(slot.x) + bvsb[j]);
                 slot.y += 1u;
                 col[top1[j] * col_stride] = slot;
-            } else if ((unsigned)s < (unsigned)S) {
+            } else if (s >= 0) {
                 const long long r = (img_region + s) * C + top1[j];
                 atomicAdd(cls_sum + r, bvsb[j]);
                 atomicAdd(cls_cnt + r, 1);

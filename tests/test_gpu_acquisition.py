@@ -227,6 +227,33 @@ def test_ids_outside_range_are_ignored_and_empty_batch():
     stats.add_batch(0, logits[:0], spx[:0], 1.0)  # empty batch is a no-op
 
 
+@pytest.mark.parametrize("path", ["tma", "ldg"])
+@pytest.mark.parametrize("bad", [-1, -7, 2 ** 31 - 1, "nseg"])
+def test_invalid_ids_before_valid_ones_do_not_leak(path, bad, monkeypatch):
+    """A thread that meets out-of-range ids BEFORE its first valid superpixel (top rows of -1 / pad / garbage) must not
+    carry anything into that superpixel: tables == the tables of the same image with those rows cut off."""
+    from mulactseg_b200 import acquisition as acq
+    monkeypatch.setenv("MAS_SCORER_PATH", path)
+    n, c, h, w, nseg = 2, 7, 40, 128, 12
+    logits = synth.logits(n, c, h, w, "cosine", seed=4, device=DEV)
+    spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=5, device=DEV, dtype=torch.int32)
+    dirty = spx.clone()
+    dirty[:, :5] = nseg if bad == "nseg" else bad
+    dirty[:, 20:22, ::3] = nseg if bad == "nseg" else bad          # and some in the middle of a column
+    got = acq.RegionStats(n, nseg, c, DEV, need_prob=False, group_bytes=0)
+    got.add_batch(0, logits, dirty, 0.1)
+    valid = (dirty >= 0) & (dirty < nseg)
+    top1 = logits.argmax(dim=1)
+    want = torch.zeros((n, nseg, c), dtype=torch.int64, device=DEV)
+    for i in range(n):
+        key = (dirty[i][valid[i]].long() * c + top1[i][valid[i]])
+        want[i] = torch.bincount(key, minlength=nseg * c).view(nseg, c)
+    assert torch.equal(got.cls_cnt.long(), want)
+    top2 = logits.topk(2, dim=1).values
+    bvsb = torch.exp((top2[:, 1] - top2[:, 0]) / 0.1) + 1e-8
+    np.testing.assert_allclose(float(got.cls_sum.double().sum()), float(bvsb[valid].double().sum()), rtol=1e-5)
+
+
 def test_argument_errors_raise():
     from mulactseg_b200 import acquisition as acq, ops
     stats = acq.RegionStats(1, 4, 6, DEV, need_prob=False)
