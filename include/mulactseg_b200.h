@@ -179,6 +179,21 @@ int mas_topk_sorted_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t
 int mas_topk_candidates_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int64_t capacity,
                                 int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
 
+/* mas_topk_candidates_msg_u64_dev -- mas_topk_candidates_u64_dev writing the MESSAGE one rank contributes to the multi-GPU
+ * merge (north_star: "global top-k merges per-GPU candidate lists with an NCCL all-gather"; replaces the host-side
+ * sorted() over the whole pool, active_selection/base.py:37): msg has capacity + 1 slots, msg[0 .. capacity) = the
+ * candidates (0 = "no key"), msg[capacity] = the count as int64 (-1 on overflow).  One all_gather_into_tensor of these
+ * messages is the only collective of the merge.
+ */
+int mas_topk_candidates_msg_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* msg, int64_t capacity,
+                                    int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* mas_merge_counts_u64_dev -- on the gathered messages (world x stride slots, stride = capacity + 1): *worst = the
+ * smallest per-rank count (-1 if any rank overflowed) and the count slots are cleared, so the whole buffer can go through
+ * mas_topk_sorted_u64_dev as plain keys.
+ */
+int mas_merge_counts_u64_dev(uint64_t* gathered, int world, int64_t stride, int32_t* worst, void* stream);
+
 /* mas_prefix_cut_dev -- how much of the ranked list RegionActiveDataset.expand_training_set consumes
  * (dataloader/region_active_dataset.py:56-66): walk sorted_keys[0 .. *count), add cost_by_tie[key & 0xffffffff] (the label
  * cost of the region: 1, or its multi-hot class count with --fair_counting --or_labeling) and stop AFTER the pick that

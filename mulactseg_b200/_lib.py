@@ -44,6 +44,8 @@ SIGNATURES = {
     "mas_topk_u64_dev": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mas_topk_sorted_u64_dev": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mas_topk_candidates_u64_dev": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mas_topk_candidates_msg_u64_dev": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mas_merge_counts_u64_dev": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "mas_sort_capacity": (c_int64, [c_int64]),
     "mas_sort_desc_u64_dev": (c_int, [c_void_p, c_int64, c_void_p]),
     "mas_acquisition_host": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_float,

@@ -148,6 +148,11 @@ class RegionStats:
             spx = spx.to(torch.int32)
         if not spx.is_contiguous():
             spx = spx.contiguous()
+        if self._prob_sum is not None and self.pixels_per_image not in (None, shape[2] * shape[3]):
+            # the class weights divide every image's probability sum by ONE pixel count (mas_class_weights_dev); the
+            # reference's per-batch torch.mean would follow a shape change, so refuse instead of weighting wrongly
+            raise RuntimeError(f"add_batch: images of {shape[2]}x{shape[3]} after images of {self.pixels_per_image} pixels: "
+                               "the predclsbal selectors need one image size per pool")
         self.pixels_per_image = shape[2] * shape[3]
         queue = self._queue
         if queue:
@@ -165,22 +170,6 @@ class RegionStats:
             self.flush()
 
 
-def predicted_class_weights(prob_sum_all: torch.Tensor, pixels_per_image: int, ref_batch: int, coeff: float) -> torch.Tensor:
-    """w_c = (coeff * pbar_c + 1)^-2 with pbar = mean over REFERENCE batches of the per-batch mean
-    probability (my_bvsb_predclsbal_pwr.py:36-47: ``cumulated += mean(prob, dim=(0,2,3))`` per batch,
-    divided by ``len(loader)``).  ``prob_sum_all`` (N,C) f64 holds per-image sums in pool order."""
-    n, c = prob_sum_all.shape
-    ref_batch = max(int(ref_batch), 1)
-    n_batches = (n + ref_batch - 1) // ref_batch
-    batch_of = torch.arange(n, device=prob_sum_all.device) // ref_batch
-    batch_sum = torch.zeros((n_batches, c), dtype=torch.float64, device=prob_sum_all.device)
-    batch_sum.index_add_(0, batch_of, prob_sum_all)
-    batch_len = torch.bincount(batch_of, minlength=n_batches).to(torch.float64)
-    batch_mean = (batch_sum / (batch_len * float(pixels_per_image)).unsqueeze(1)).to(torch.float32)
-    pbar = batch_mean.sum(dim=0) / float(n_batches)
-    return (float(coeff) * pbar + 1.0) ** (-2)
-
-
 def finalize(stats: RegionStats, spec: SelectorSpec, coeff: float = 0.0, ref_batch: int = 1, group=None, shard_counts=None):
     """Selector epilogue -> (scores (n,S) f32, dominant (n,S) i32) on the device.
 
@@ -194,10 +183,7 @@ def finalize(stats: RegionStats, spec: SelectorSpec, coeff: float = 0.0, ref_bat
         if stats.prob_sum is None:
             raise RuntimeError("predclsbal weighting needs RegionStats(need_prob=True)")
         prob_all = mdist.all_gather_rows(stats.prob_sum, group, shard_counts)
-        if prob_all.is_cuda:
-            weight = ops.class_weights(prob_all.contiguous(), stats.pixels_per_image, ref_batch, coeff)
-        else:       # gloo / CPU tensors in the host-logic tests
-            weight = predicted_class_weights(prob_all, stats.pixels_per_image, ref_batch, coeff).contiguous()
+        weight = ops.class_weights(prob_all.contiguous(), stats.pixels_per_image, ref_batch, coeff)
     score, _, dominant = ops.region_scores(stats.cls_sum, stats.cls_cnt, weight)
     minmax = None
     if spec.normalise:

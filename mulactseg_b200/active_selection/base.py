@@ -83,6 +83,11 @@ class RegionSelector(object):
                 images = batch["images"].to(device, dtype=torch.float32, non_blocking=True)
                 spx = batch["spx"].to(torch.int32).to(device, non_blocking=True)
                 preds = model(images)                      # (B, C', H, W) -- stays PyTorch
+                if preds.dtype not in (torch.float32, torch.bfloat16):
+                    preds = preds.float()                  # fp16 / fp64 heads: the reference's ops take any float dtype
+                b_, c_, h_, w_ = preds.shape
+                if preds.stride(3) != 1 or preds.stride(2) != w_ or preds.stride(1) != h_ * w_:
+                    preds = preds.contiguous()             # channels_last / sliced outputs: one copy, like .softmax would make
                 if self.spec.slice_ignore and predignore:
                     preds = preds[:, :-1]                  # read in place through the image stride
                 if stats is None:
@@ -136,10 +141,12 @@ class RegionSelector(object):
         ps = self.score_regions(trainer, pool_set)
 
         if getattr(self.args, "save_scores", False):   # base.py:31-34 (needs the full list)
-            full = self.gen_score_list_from_tensor(pool_set, mdist.all_gather_rows(ps.scores, self.group))
-            fname = os.path.join(trainer.model_save_dir, "AL_record", "region_val_{}.json".format(trainer.selection_iter))
-            with open(fname, "w") as f:
-                json.dump(full, f)
+            gathered = mdist.all_gather_rows(ps.scores, self.group)       # collective: every rank takes part ...
+            if mdist.rank_world(self.group)[0] == 0:                      # ... one rank writes
+                full = self.gen_score_list_from_tensor(pool_set, gathered)
+                fname = os.path.join(trainer.model_save_dir, "AL_record", "region_val_{}.json".format(trainer.selection_iter))
+                with open(fname, "w") as f:
+                    json.dump(full, f)
 
         n_pool = sum(len(v) for v in pool_set.suppix.values())
         fair = getattr(active_set.args, "fair_counting", False) and getattr(active_set.args, "or_labeling", False)

@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/mulactseg_b200.h"
 
 namespace mas {
@@ -38,17 +40,44 @@ inline int cuda_fail(cudaError_t e, const char* what) {
         }                                     \
     } while (0)
 
+// ---- per-device launch state.  One process may drive several GPUs (and several host threads): everything a launcher
+// caches (SM count, occupancy, "dynamic shared memory opted in") is keyed by the CURRENT device and held in atomics --
+// racing threads compute the same value, so a lost update is harmless.
+constexpr int kMaxDevices = 64;
+
+inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+    return dev;
+}
+
+// one int per device, 0 = "not computed yet"
+struct PerDeviceInt {
+    std::atomic<int> v[kMaxDevices];
+    PerDeviceInt() { for (auto& x : v) x.store(0, std::memory_order_relaxed); }
+    int get(int dev) const { return v[dev].load(std::memory_order_relaxed); }
+    void set(int dev, int value) { v[dev].store(value, std::memory_order_relaxed); }
+};
+
 inline int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            return 148;
+    static PerDeviceInt cached;
+    const int dev = current_device();
+    int n = cached.get(dev);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+        cached.set(dev, n);
     }
-    return cached;
+    return n;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: opt in once per (kernel, device)
+template <typename K>
+inline cudaError_t opt_in_smem(K kernel, PerDeviceInt& done, int bytes) {
+    const int dev = current_device();
+    if (done.get(dev) >= bytes) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.set(dev, bytes);
+    return e;
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {

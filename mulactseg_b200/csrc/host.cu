@@ -55,6 +55,19 @@ struct HostContext {
     }
 };
 
+// Error paths of the host entry points return while H2D copies from the CALLER's buffers may still be in flight: drain both
+// streams before the caller gets its buffers back (the success path ends with its own synchronize and disarms the guard).
+struct DrainOnExit {
+    HostContext& d;
+    bool armed = true;
+    explicit DrainOnExit(HostContext& ctx) : d(ctx) {}
+    ~DrainOnExit() {
+        if (!armed) return;
+        if (d.copy) cudaStreamSynchronize(d.copy);
+        if (d.compute) cudaStreamSynchronize(d.compute);
+    }
+};
+
 HostContext* context_for_current_device() {
     static std::mutex table_lock;
     static std::map<int, HostContext*> table;
@@ -95,6 +108,7 @@ extern "C" int mas_acquisition_host(const void* logits, int logits_dtype, const 
     std::lock_guard<std::mutex> guard(ctx->lock);
     HostContext& d = *ctx;
     MAS_CUDA_OK(d.init());
+    DrainOnExit drain(d);
     d.begin();
     char* stage_logits[2];
     int32_t* stage_ids[2];
@@ -188,6 +202,7 @@ extern "C" int mas_acquisition_host(const void* logits, int logits_dtype, const 
     MAS_CUDA_OK(cudaMemcpyAsync(score, d_score, (size_t)n_regions * sizeof(float), cudaMemcpyDeviceToHost, d.compute));
     if (dominant) MAS_CUDA_OK(cudaMemcpyAsync(dominant, d_dom, (size_t)n_regions * sizeof(int32_t), cudaMemcpyDeviceToHost, d.compute));
     MAS_CUDA_OK(cudaStreamSynchronize(d.compute));
+    drain.armed = false;    // every copy was issued on / waited for by the compute stream
     return 0;
 }
 
@@ -202,6 +217,7 @@ extern "C" int mas_select_topk_host(const float* score, const uint8_t* in_pool, 
     std::lock_guard<std::mutex> guard(ctx->lock);
     HostContext& d = *ctx;
     MAS_CUDA_OK(d.init());
+    DrainOnExit drain(d);
     d.begin();
     d.next = 16;   // slots 16.. : keeps the acquisition buffers of the same process untouched
     while (d.slots.size() < 16) d.slots.push_back(HostContext::Slot());
@@ -226,5 +242,6 @@ extern "C" int mas_select_topk_host(const float* score, const uint8_t* in_pool, 
     MAS_CUDA_OK(cudaMemcpyAsync(out_keys, d_out, k * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.compute));
     MAS_CUDA_OK(cudaMemcpyAsync(out_count, d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, d.compute));
     MAS_CUDA_OK(cudaStreamSynchronize(d.compute));
+    drain.armed = false;
     return 0;
 }

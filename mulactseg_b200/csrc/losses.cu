@@ -544,18 +544,21 @@ cudaError_t launch_one(LossParams p, bool backward, bool accurate, cudaStream_t 
     // forward: running maxima (u64) + softmax numerators (f32) per (class, thread); backward: the numerators
     const size_t smem = (size_t)p.C * kThreads * (backward ? sizeof(float) : sizeof(unsigned long long) + sizeof(float));
     // persistent grid: one wave of resident CTAs (per instantiation; the generic channel padding changes smem by < 2x)
-    static int per_sm[3] = {0, 0, 0};
+    static mas::PerDeviceInt occ[3];     // per instantiation and device
     const int which = backward ? 0 : (accurate ? 1 : 2);
-    if (per_sm[which] == 0) {
+    const int dev = mas::current_device();
+    int per_sm_now = occ[which].get(dev);
+    if (per_sm_now == 0) {
         const size_t smem_max = (size_t)CMAX * kThreads * (backward ? sizeof(float) : sizeof(unsigned long long) + sizeof(float));
-        if (backward) per_sm[which] = resident_ctas(multihot_loss_bwd_kernel<CMAX, EXACT, IdT>, smem_max);
-        else if (accurate) per_sm[which] = resident_ctas(multihot_loss_fwd_kernel<CMAX, EXACT, IdT, true>, smem_max);
-        else per_sm[which] = resident_ctas(multihot_loss_fwd_kernel<CMAX, EXACT, IdT, false>, smem_max);
+        if (backward) per_sm_now = resident_ctas(multihot_loss_bwd_kernel<CMAX, EXACT, IdT>, smem_max);
+        else if (accurate) per_sm_now = resident_ctas(multihot_loss_fwd_kernel<CMAX, EXACT, IdT, true>, smem_max);
+        else per_sm_now = resident_ctas(multihot_loss_fwd_kernel<CMAX, EXACT, IdT, false>, smem_max);
+        occ[which].set(dev, per_sm_now);
     }
     // Tile height: the cost of a tile is the number of its rows that hold selected pixels, served one after the other by
     // ONE warp, so short tiles spread the selected superpixels over more warps (what matters when few pixels are
     // labelled); tall tiles flush the private maxima less often.  Aim at >= 8 tiles per resident warp.
-    const long long warps = (long long)mas::sm_count() * per_sm[which] * (kThreads / 32);
+    const long long warps = (long long)mas::sm_count() * per_sm_now * (kThreads / 32);
     const long long strips = (long long)p.n_img * ((p.W + 31) / 32);
     int rows = kTileRows;
     while (rows > 4 && strips * ((p.H + rows - 1) / rows) < 8 * warps) rows >>= 1;
@@ -563,7 +566,7 @@ cudaError_t launch_one(LossParams p, bool backward, bool accurate, cudaStream_t 
     p.tile_rows = rows;
     const long long tiles = strips * ((p.H + rows - 1) / rows);
     const long long want = (tiles + kThreads / 32 - 1) / (kThreads / 32);
-    const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)mas::sm_count() * per_sm[which]));
+    const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)mas::sm_count() * per_sm_now));
     if (backward) {
         multihot_loss_bwd_kernel<CMAX, EXACT, IdT><<<blocks, kThreads, smem, stream>>>(p);
     } else {

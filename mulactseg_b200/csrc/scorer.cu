@@ -494,8 +494,13 @@ template <int CMAX, bool EXACT, int VEC, bool NEED_PROB, typename T>
 cudaError_t launch_ldg(StatsParams p, cudaStream_t stream) {
     auto kernel = bvsb_stats_ldg_kernel<CMAX, EXACT, VEC, NEED_PROB, T>;
     const size_t smem = (size_t)p.C * kLdgThreads * sizeof(uint2);
-    static int per_sm = 0;   // per instantiation; smem differs by at most the generic channel padding
-    if (per_sm == 0) per_sm = resident_blocks(kernel, kLdgThreads, (size_t)CMAX * kLdgThreads * sizeof(uint2));
+    static mas::PerDeviceInt occ;   // per instantiation and device; smem differs by at most the generic channel padding
+    const int dev = mas::current_device();
+    int per_sm = occ.get(dev);
+    if (per_sm == 0) {
+        per_sm = resident_blocks(kernel, kLdgThreads, (size_t)CMAX * kLdgThreads * sizeof(uint2));
+        occ.set(dev, per_sm);
+    }
     p.strips = (p.W + 32 * VEC - 1) / (32 * VEC);
     p.total_rows = (long long)p.n_img * p.strips * p.H;
     // one wave of resident CTAs; never fewer than ~8 rows per warp
@@ -514,10 +519,9 @@ cudaError_t launch_tma(StatsParams p, cudaStream_t stream, bool* unsupported) {
     const size_t elt = sizeof(T);
     const uint32_t stage_bytes = (uint32_t)p.C * kTmaStripPx * elt + kTmaStripPx * 4;
     const size_t col_bytes_per_warp = (size_t)p.C * 32 * sizeof(uint2);
-    int dev = 0, max_smem = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
-        return cudaSuccess;
+    const int dev = mas::current_device();
+    int max_smem = 0;
+    if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return cudaSuccess;
     int stages = env_int("MAS_SCORER_STAGES", 0);
     int warps = env_int("MAS_SCORER_WARPS", 0);
     if (stages <= 0) stages = (elt == 2) ? 4 : 2;
@@ -569,19 +573,20 @@ cudaError_t launch_tma(StatsParams p, cudaStream_t stream, bool* unsupported) {
     *unsupported = false;
 
     auto kernel = bvsb_stats_tma_kernel<CMAX, EXACT, NEED_PROB, T>;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+    static mas::PerDeviceInt configured;      // per instantiation AND device (the attribute is a per-device setting)
+    {
+        cudaError_t e = mas::opt_in_smem(kernel, configured, (int)max_smem);
         if (e != cudaSuccess) return e;
-        configured = (size_t)max_smem;
     }
     // one wave of resident CTAs: with fewer warps per CTA several CTAs share an SM, and a CTA of the NEXT launch can move
-    // in as soon as one of them retires (finer hand-over between consecutive launches on the two launch lanes)
-    static size_t occ_smem = 0;      // per instantiation: the occupancy query is not free on the launch path
-    static int occ_warps = 0, per_sm = 1;
-    if (occ_smem != smem || occ_warps != warps) {
+    // in as soon as one of them retires (finer hand-over between consecutive launches on the two launch lanes).
+    // The occupancy query is not free on the launch path: cached per (device, warps) -- smem is a function of warps,
+    // stages and C, of which only `warps` varies between launches of one instantiation unless the env switches change.
+    static mas::PerDeviceInt occ[kTmaMaxWarps + 1], occ_key[kTmaMaxWarps + 1];
+    int per_sm = occ[warps].get(dev);
+    if (per_sm == 0 || occ_key[warps].get(dev) != (int)smem) {
         per_sm = resident_blocks(kernel, warps * 32, smem);
-        occ_smem = smem; occ_warps = warps;
+        occ[warps].set(dev, per_sm); occ_key[warps].set(dev, (int)smem);
     }
     const long long cap = (p.total_rows + 8 * warps - 1) / (8 * warps);
     const long long blocks = std::max<long long>(1, std::min<long long>((long long)mas::sm_count() * per_sm, cap));

@@ -182,9 +182,27 @@ __global__ void __launch_bounds__(256) fast_compact_kernel(const unsigned long l
     }
 }
 
-__global__ void fast_finish_kernel(const FastState* st, int32_t* out_count, long long k, long long capacity, int clamp) {
+__global__ void fast_finish_kernel(const FastState* st, int32_t* out_count, long long k, long long capacity, int clamp,
+                                   long long* msg_count) {
     const long long c = st->count;
-    *out_count = c > capacity ? -1 : (int32_t)(clamp ? min(c, k) : c);
+    const int32_t result = c > capacity ? -1 : (int32_t)(clamp ? min(c, k) : c);
+    *out_count = result;
+    if (msg_count) *msg_count = (long long)result;      // the count travels in the slot after the candidates
+}
+
+// Multi-GPU merge: the all-gathered buffer holds, per rank, `stride - 1` candidate slots followed by that rank's count
+// (-1 = its buffer overflowed).  One warp reduces the counts to their minimum and clears the count slots, so that the
+// whole buffer can be handed to the bucket select as plain keys (0 = "no key").
+__global__ void merge_counts_kernel(unsigned long long* gathered, int world, long long stride, int32_t* worst) {
+    long long mine = 0x7fffffffll;
+    for (int r = threadIdx.x; r < world; r += 32) {
+        unsigned long long* slot = gathered + (long long)r * stride + (stride - 1);
+        mine = min(mine, (long long)*slot);
+        *slot = 0ull;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+    if (threadIdx.x == 0) *worst = (int32_t)mine;
 }
 
 // ---------------------------------------------------------------------------------------- budget cut
@@ -307,12 +325,10 @@ __global__ void sort_global_step2_kernel(unsigned long long* keys, long long n_p
 }
 
 cudaError_t sort_configure() {
-    static bool done = false;
-    if (done) return cudaSuccess;
+    static mas::PerDeviceInt done_tile, done_merge;     // the opt-in is a per-device setting
     const int bytes = kSortTile * (int)sizeof(unsigned long long);
-    cudaError_t e = cudaFuncSetAttribute(sort_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sort_tile_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    done = e == cudaSuccess;
+    cudaError_t e = mas::opt_in_smem(sort_tile_kernel, done_tile, bytes);
+    if (e == cudaSuccess) e = mas::opt_in_smem(sort_tile_merge_kernel, done_merge, bytes);
     return e;
 }
 
@@ -405,7 +421,7 @@ namespace {
 
 // histograms + compaction: out[0 .. count) holds every key from the 24-bit prefix of the k-th largest key upwards
 int fast_candidates(const char* what, const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int64_t capacity, int32_t* out_count,
-                    void* workspace, size_t workspace_bytes, void* stream, bool clamp_count) {
+                    void* workspace, size_t workspace_bytes, void* stream, bool clamp_count, long long* msg_count = nullptr) {
     MAS_REQUIRE(keys && out && out_count && workspace, MAS_E_BADARG, "%s: null pointer", what);
     MAS_REQUIRE(n >= 0 && k >= 0, MAS_E_BADARG, "%s: negative size", what);
     MAS_REQUIRE(workspace_bytes >= mas_topk_workspace_bytes(), MAS_E_WORKSPACE, "%s: workspace too small", what);
@@ -423,7 +439,7 @@ int fast_candidates(const char* what, const uint64_t* keys, int64_t n, int64_t k
         fast_compact_kernel<<<blocks, 256, 0, st>>>(kk, n, state, reinterpret_cast<unsigned long long*>(out), capacity);
         mas::count_launches(3);
     }
-    fast_finish_kernel<<<1, 1, 0, st>>>(state, out_count, k, capacity, clamp_count ? 1 : 0);
+    fast_finish_kernel<<<1, 1, 0, st>>>(state, out_count, k, capacity, clamp_count ? 1 : 0, msg_count);
     mas::count_launches(1);
     MAS_LAUNCH_OK(what);
     return 0;
@@ -434,6 +450,22 @@ int fast_candidates(const char* what, const uint64_t* keys, int64_t n, int64_t k
 extern "C" int mas_topk_candidates_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int64_t capacity,
                                            int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
     return fast_candidates("topk_candidates_u64", keys, n, k, out, capacity, out_count, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int mas_topk_candidates_msg_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* msg, int64_t capacity,
+                                               int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    MAS_REQUIRE(msg, MAS_E_BADARG, "topk_candidates_msg_u64: null pointer");
+    return fast_candidates("topk_candidates_msg_u64", keys, n, k, msg, capacity, out_count, workspace, workspace_bytes, stream, false,
+                           reinterpret_cast<long long*>(msg) + capacity);
+}
+
+extern "C" int mas_merge_counts_u64_dev(uint64_t* gathered, int world, int64_t stride, int32_t* worst, void* stream) {
+    MAS_REQUIRE(gathered && worst, MAS_E_BADARG, "merge_counts_u64: null pointer");
+    MAS_REQUIRE(world >= 1 && stride >= 2, MAS_E_BADARG, "merge_counts_u64: bad shape");
+    merge_counts_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(gathered), world, stride, worst);
+    mas::count_launches(1);
+    MAS_LAUNCH_OK("merge_counts_kernel");
+    return 0;
 }
 
 extern "C" int mas_topk_sorted_u64_dev(const uint64_t* keys, int64_t n, int64_t k, uint64_t* out, int64_t capacity,

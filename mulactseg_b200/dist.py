@@ -40,7 +40,8 @@ def shard_sizes(n_items: int, world: int) -> List[int]:
 
 def all_gather_rows(local: torch.Tensor, group=None, counts: Optional[List[int]] = None) -> torch.Tensor:
     """Concatenate per-rank (n_r, ...) tensors along dim 0 in rank order (n_r may differ by rank).
-    ``counts`` = the n_r of every rank when the caller knows them (``shard_sizes``): saves a collective and a host sync."""
+    ``counts`` = the n_r of every rank when the caller knows them (``shard_sizes``): saves a collective and a host sync.
+    ONE ``all_gather_into_tensor`` into a single (world, width, ...) buffer; with equal shards the result is a view of it."""
     if not is_distributed(group):
         return local
     world = td.get_world_size(group)
@@ -52,21 +53,28 @@ def all_gather_rows(local: torch.Tensor, group=None, counts: Optional[List[int]]
     elif len(counts) != world or counts[td.get_rank(group)] != local.shape[0]:
         raise RuntimeError(f"all_gather_rows: counts {counts} do not match this rank's {local.shape[0]} rows")
     width = max(counts)
-    padded = local.new_zeros((width,) + tuple(local.shape[1:]))
-    padded[: local.shape[0]] = local
-    parts = [torch.empty_like(padded) for _ in range(world)]
-    td.all_gather(parts, padded.contiguous(), group=group)
-    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+    rest = tuple(local.shape[1:])
+    if local.shape[0] == width:
+        padded = local.contiguous()
+    else:
+        padded = local.new_zeros((width,) + rest)
+        padded[: local.shape[0]] = local
+    out = local.new_empty((world * width,) + rest)       # concatenated layout (what gloo accepts as well as NCCL)
+    td.all_gather_into_tensor(out, padded, group=group)
+    if min(counts) == width:
+        return out
+    boxes = out.view((world, width) + rest)
+    return torch.cat([boxes[r, :c] for r, c in enumerate(counts)], dim=0)
 
 
 def all_reduce_minmax(minmax: torch.Tensor, group=None) -> torch.Tensor:
-    """[min, max] pairs reduced over the ranks (+inf / -inf from an empty shard are neutral)."""
+    """[min, max] pairs reduced over the ranks (+inf / -inf from an empty shard are neutral): one MAX all-reduce of
+    [-min, max]."""
     if not is_distributed(group):
         return minmax
-    lo, hi = minmax[:1].clone(), minmax[1:].clone()
-    td.all_reduce(lo, op=td.ReduceOp.MIN, group=group)
-    td.all_reduce(hi, op=td.ReduceOp.MAX, group=group)
-    return torch.cat([lo, hi]).contiguous()
+    both = torch.stack([-minmax[0], minmax[1]])
+    td.all_reduce(both, op=td.ReduceOp.MAX, group=group)
+    return torch.stack([-both[0], both[1]]).contiguous()
 
 
 def all_reduce_min(t: torch.Tensor, group=None) -> torch.Tensor:
@@ -81,17 +89,25 @@ def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
     return t
 
 
+def gather_messages(msg: torch.Tensor, group=None) -> torch.Tensor:
+    """Every rank's fixed-size message -> one (world, len(msg)) tensor on every rank: a single
+    ``all_gather_into_tensor`` into one buffer (no per-rank list, no concatenation).  The top-k merge sends each rank's
+    candidate keys with their count in the last slot this way (``mas_topk_candidates_msg_u64_dev``)."""
+    if not is_distributed(group):
+        return msg.view(1, -1)
+    world = td.get_world_size(group)
+    out = msg.new_empty(world * msg.numel())
+    td.all_gather_into_tensor(out, msg.contiguous().view(-1), group=group)
+    return out.view(world, msg.numel())
+
+
 def gather_candidates(keys: torch.Tensor, count: torch.Tensor, k: int, group=None) -> torch.Tensor:
     """All ranks' candidate keys -> one flat int64 tensor on every rank (unused slots are 0 = 'no key').
 
     ``keys`` holds this rank's candidates in its first ``count`` slots, ``count`` <= k (anything after is ignored).
+    Used by the exact fallback of the merge (``selection.top_regions``).
     """
     local = keys[:k].clone()
     slot = torch.arange(k, device=keys.device)
     local = torch.where(slot < count.to(torch.int64), local, torch.zeros_like(local))
-    if not is_distributed(group):
-        return local
-    world = td.get_world_size(group)
-    parts = [torch.empty_like(local) for _ in range(world)]
-    td.all_gather(parts, local.contiguous(), group=group)
-    return torch.cat(parts)
+    return gather_messages(local, group).reshape(-1)

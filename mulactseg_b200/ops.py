@@ -251,6 +251,32 @@ def topk_sorted(keys: torch.Tensor, k: int, sort: bool = True) -> Tuple[torch.Te
     return out, count
 
 
+def topk_candidates_msg(keys: torch.Tensor, k: int) -> torch.Tensor:
+    """This rank's message for the multi-GPU top-k merge (``mas_topk_candidates_msg_u64_dev``): ``sort_capacity(k) + 1``
+    int64 slots = an unordered superset of the k largest keys (0 = no key) followed by their count (-1 = overflow)."""
+    _want(keys, "keys", torch.int64, 1)
+    k = int(k)
+    cap = sort_capacity(max(k, 1))
+    msg = torch.empty(cap + 1, dtype=torch.int64, device=keys.device)
+    count = torch.empty(1, dtype=torch.int32, device=keys.device)
+    ws_bytes = int(_lib.load().mas_topk_workspace_bytes())
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+    with _on(keys):
+        _lib.call("mas_topk_candidates_msg_u64_dev", keys.data_ptr(), keys.numel(), k, msg.data_ptr(), cap, count.data_ptr(),
+                  ws.data_ptr(), ws_bytes, _stream(keys))
+    return msg
+
+
+def merge_counts(gathered: torch.Tensor, worst: torch.Tensor) -> None:
+    """(world, cap + 1) gathered messages: worst[0] <- the smallest per-rank count (-1 if any rank overflowed); the count
+    slots are cleared in place so that ``gathered.view(-1)`` is a plain key list (``mas_merge_counts_u64_dev``)."""
+    _want(gathered, "gathered", torch.int64, 2)
+    _want(worst, "worst", torch.int32, 1)
+    with _on(gathered):
+        _lib.call("mas_merge_counts_u64_dev", gathered.data_ptr(), gathered.shape[0], gathered.shape[1], worst.data_ptr(),
+                  _stream(gathered))
+
+
 def topk_keys(keys: torch.Tensor, k: int, sort: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """The k largest non-zero keys (sorted descending if ``sort``) and a device int32 count.
 

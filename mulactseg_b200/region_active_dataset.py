@@ -19,6 +19,16 @@ import pickle
 from typing import Dict, List
 
 
+def _is_writer() -> bool:
+    """Under torchrun every rank walks the same ranked list (each keeps its own pool / label bookkeeping in step), but
+    files and wandb records are written by rank 0 only."""
+    try:
+        import torch.distributed as td
+        return not (td.is_available() and td.is_initialized()) or td.get_rank() == 0
+    except Exception:
+        return True
+
+
 class RegionActiveDataset:
     def __init__(self, args, trg_pool_dataset, trg_label_dataset):
         self.args = args
@@ -83,12 +93,12 @@ class RegionActiveDataset:
         if emptied:
             pool.im_idx[:] = [k for k in pool.im_idx if tuple(k) not in emptied]
 
-        if exceeded:
+        if exceeded and _is_writer():
             fname = f"{selection_method}_selection_{self.selection_iter:02d}.pkl"
             with open(os.path.join(self.args.model_save_dir, fname), "wb") as f:
                 pickle.dump(sample_region[:taken], f)
             print(taken)
-        wandb = getattr(self.args, "wandb", None)
+        wandb = getattr(self.args, "wandb", None) if _is_writer() else None
         if wandb is not None:                      # :75-80
             global_step = int(self.args.finetune_itrs) * (self.selection_iter - 1)
             wandb.log({"num_selected_spx": taken, "num_cls_spx": selection_count / taken, "sampling_iter": self.selection_iter},
@@ -97,6 +107,8 @@ class RegionActiveDataset:
 
     # ------------------------------------------------------------------ persistence (identical files)
     def dump_datalist(self):
+        if not _is_writer():
+            return
         path = os.path.join(self.args.model_save_dir, f"datalist_{self.selection_iter:02d}.pkl")
         with open(path, "wb") as f:
             pickle.dump({"trg_label_im_idx": self.trg_label_dataset.im_idx, "trg_pool_im_idx": self.trg_pool_dataset.im_idx,

@@ -61,29 +61,54 @@ def decode_keys(keys: np.ndarray, nseg: int, im_idx: Sequence[Sequence[str]], ra
     return out
 
 
+_pinned = {}
+
+
+def _pinned_buffers(device, k: int):
+    """Pinned host landing zone of a round's result (k keys + [n_take, worst]), allocated once per (device, k)."""
+    key = (str(device), int(k))
+    buf = _pinned.get(key)
+    if buf is None:
+        buf = _pinned[key] = (torch.empty(k, dtype=torch.int64).pin_memory(), torch.empty(2, dtype=torch.int32).pin_memory())
+    return buf
+
+
+def _ranked_to_host(best: torch.Tensor, take: torch.Tensor, worst: Optional[torch.Tensor], k: int):
+    """ONE host sync per round: the ranked keys (first k slots) and the two control words land in pinned memory through
+    two async copies on the current stream, then a single stream synchronize.  -> (keys view, n_take, worst)."""
+    h_keys, h_meta = _pinned_buffers(best.device, k)
+    meta = torch.stack([take.reshape(()), (worst if worst is not None else take).reshape(())])
+    h_meta.copy_(meta, non_blocking=True)
+    h_keys.copy_(best[:k], non_blocking=True)
+    torch.cuda.current_stream(best.device).synchronize()
+    return h_keys, int(h_meta[0]), int(h_meta[1])
+
+
 def top_regions(scores: torch.Tensor, in_pool: torch.Tensor, image_rank_local: torch.Tensor, k: int, group=None,
                 cost_by_tie: Optional[torch.Tensor] = None, budget: Optional[int] = None):
     """Sorted (descending) keys of the k best pool regions over ALL ranks, as a host uint64 array.
 
     scores / in_pool: this rank's (n_local, S) shard; image_rank_local: global ranks of its images.
-    Per rank: key -> candidate superset of its k best (<= sort_capacity(k) slots) -> all_gather -> select + sort k on
-    every rank; no host sync before the final count.
+    Per rank: key -> candidate superset of its k best with the count in the last slot (one message of
+    ``sort_capacity(k) + 1`` slots) -> ONE ``all_gather_into_tensor`` -> counts reduced / cleared on the device ->
+    select + sort k on every rank -> one host sync for the result.
     With ``cost_by_tie`` (uint8 device table of label costs indexed by image rank * S + id, see ``region_cost_table``)
     and ``budget`` the list is cut on the device where ``expand_training_set`` would stop (``mas_prefix_cut_dev``) and
-    only that prefix travels to the host.
+    only that prefix is decoded on the host.
     """
     local_keys = ops.region_keys(scores, in_pool, image_rank_local)
     distributed = mdist.is_distributed(group)
     keys, worst = local_keys, None
     if distributed:
-        # per GPU: an unordered superset of its k best keys (two histograms + compaction, no sort)
-        local, count = ops.topk_sorted(local_keys, k, sort=False)
-        worst = mdist.all_reduce_min(count.to(torch.int64), group)       # -1 if the buffer overflowed on any rank
-        keys = mdist.gather_candidates(local, count, local.numel(), group)
-    best, count = ops.topk_sorted(keys, k)           # two bucket histograms + compaction + sort
+        gathered = mdist.gather_messages(ops.topk_candidates_msg(local_keys, k), group)
+        worst = torch.empty(1, dtype=torch.int32, device=scores.device)
+        ops.merge_counts(gathered, worst)                # -1 if the buffer overflowed on any rank
+        keys = gathered.view(-1)
+    best, count = ops.topk_sorted(keys, k)               # two bucket histograms + compaction + sort
     take = ops.prefix_cut(best, count, cost_by_tie, budget) if cost_by_tie is not None else count
-    n = int(take.item())
-    if n < 0 or (worst is not None and int(worst.item()) < 0):
+    k_host = min(int(k), best.numel())
+    host, n, bad = _ranked_to_host(best, take, worst, k_host)
+    if n < 0 or bad < 0:
         # massively tied scores overflowed a candidate buffer somewhere: every rank redoes the exact radix select
         keys = local_keys
         if distributed:
@@ -91,8 +116,8 @@ def top_regions(scores: torch.Tensor, in_pool: torch.Tensor, image_rank_local: t
             keys = mdist.gather_candidates(local, count, k, group)
         best, count = ops.topk_keys(keys, k, sort=True)
         take = ops.prefix_cut(best, count, cost_by_tie, budget) if cost_by_tie is not None else count
-        n = int(take.item())
-    return best[:n].cpu().numpy().view(np.uint64)
+        host, n, _ = _ranked_to_host(best, take, None, k_host)
+    return host[:n].numpy().copy().view(np.uint64)
 
 
 def region_cost_table(costs_by_image: np.ndarray, rank: np.ndarray, device) -> torch.Tensor:

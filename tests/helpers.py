@@ -50,3 +50,16 @@ def assert_scores_close(got, ref, normalised, msg=""):
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5 if normalised else 1e-12, err_msg=msg)
+
+
+def class_weights_ref(prob_sum_all, pixels_per_image, ref_batch, coeff):
+    """Test-side restatement of my_bvsb_predclsbal_pwr.py:36-47 on per-image probability sums (N,C) f64 in pool order:
+    ``cumulated += mean(prob, dim=(0,2,3))`` per REFERENCE batch in fp32, ``/ len(loader)``, ``(coeff * p + 1) ** -2``."""
+    prob = torch.as_tensor(prob_sum_all, dtype=torch.float64)
+    cumulated = torch.zeros(prob.shape[1], dtype=torch.float32)
+    n_batches = 0
+    for b0 in range(0, prob.shape[0], ref_batch):
+        part = prob[b0:b0 + ref_batch]
+        cumulated += (part.sum(dim=0) / (part.shape[0] * pixels_per_image)).to(torch.float32)
+        n_batches += 1
+    return (float(coeff) * (cumulated / n_batches) + 1.0) ** (-2)

@@ -10,7 +10,8 @@ import torch
 import torch.distributed as td
 import torch.multiprocessing as mp
 
-from mulactseg_b200 import acquisition as acq, dist as mdist, selection
+from helpers import class_weights_ref
+from mulactseg_b200 import dist as mdist, selection
 
 
 def _free_port():
@@ -38,9 +39,8 @@ def _worker(rank, world, port, n_img, nseg, c, k, out_dir):
         assert torch.equal(gathered, known)                      # known shard sizes: same rows, no size exchange
         worst = mdist.all_reduce_min(torch.tensor([5 - 6 * rank], dtype=torch.int64))
         assert int(worst) == 5 - 6 * (world - 1)
-        w_dist = acq.predicted_class_weights(gathered, 1000, 4, 6.0)
-        w_one = acq.predicted_class_weights(prob_sum, 1000, 4, 6.0)
-        assert torch.equal(w_dist, w_one)
+        assert torch.equal(gathered, prob_sum)                   # pool order restored: the class weights follow
+        assert torch.equal(class_weights_ref(gathered, 1000, 4, 6.0), class_weights_ref(prob_sum, 1000, 4, 6.0))
 
         # (2) min over non-zero / max
         shard = scores[lo:hi]
@@ -67,6 +67,12 @@ def _worker(rank, world, port, n_img, nseg, c, k, out_dir):
         buf[: len(mine)] = torch.from_numpy(mine.view(np.int64))
         count = torch.tensor([int((mine != 0).sum())], dtype=torch.int32)
         merged = mdist.gather_candidates(buf, count, k).numpy().view(np.uint64)
+        # the fast path's message: candidates + count in the last slot, one all_gather_into_tensor, counts cleared after
+        msg = torch.cat([buf, count.to(torch.int64)])
+        boxes = mdist.gather_messages(msg).clone()
+        assert boxes.shape == (world, k + 1) and int(boxes[rank, k]) == int(count)
+        boxes[:, k] = 0
+        np.testing.assert_array_equal(np.sort(boxes[:, :k].reshape(-1).numpy().view(np.uint64)), np.sort(merged))
         best = np.sort(merged)[::-1][:k]
         best = best[best != 0]                                   # k may exceed the number of pool regions
         want = np.sort(keys_of(scores, in_pool, 0))[::-1][:k]
