@@ -4,27 +4,39 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
 
-Workload (BASELINE.json configs[1]): one ``my_bvsb_predclsbal_pwr`` acquisition round over a synthetic
+Headline workload (BASELINE.json configs[1]): one ``my_bvsb_predclsbal_pwr`` acquisition round over a synthetic
 Cityscapes-shaped pool -- 1024x2048 logits with 19 classes (fp32), 2048 superpixels per image,
 ``val_batch_size`` 4, ``cls_weight_coeff`` 6, T = 0.1, budget 100 000 class-units with fair counting --
 sharded by image: 372 images per GPU (2975 / 8 rounded up), so N = 8 is the full pool (weak scaling).
 A *step* is one whole round over the resident shard: zero the tables, stream every image's logits through
-the fused scorer (one launch per batch of 4 images, as the selector plugin does), class weights (NCCL
-all-gather of the per-image class-probability sums), per-region scores, per-GPU top-(budget+1) radix
-select, NCCL all-gather of the candidates, merge + sort, cut the ranked list where the cumulative label cost exceeds
+the fused scorer (``add_batch`` per loader batch of 4 images, as the selector plugin does), class weights (NCCL
+all-gather of the per-image class-probability sums), per-region scores, per-GPU candidate select, ONE NCCL
+all-gather of the candidate messages, merge + sort, cut the ranked list where the cumulative label cost exceeds
 the budget (on the device) and copy the winners to the host.  ``value`` = regions scored+selected per second over all GPUs.
+
+The same JSON line carries
+  * ``parity``    -- the GPU path checked INSIDE this run against the CPU port on the first images of the shard
+                     (per-region scores 1e-5, selected region set), and under --gpus N a cross-rank hash of the final
+                     ranking plus a sharded mini-round recomputed on one rank;
+  * ``secondary`` -- the other BASELINE.json configs, each with ms, algorithmic bytes, roofline fraction, a CPU baseline
+                     from the oracle port on a bounded sample and its own parity block: configs[2] VOC-shaped pool
+                     (375x500 native and the reference's 513x513 crop; under --gpus N too), the scorer on bf16 logits,
+                     configs[3] stage-1 loss step at rho 0.02 / 0.2 / 1.0, configs[4] prototype labeller (Cityscapes, VOC).
 
 One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement" for every field.
 """
 from __future__ import annotations
 
 import argparse
+import dataclasses
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+import types
+import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -32,21 +44,56 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-H, W, C, NSEG = 1024, 2048, 19, 2048
-TEMP, COEFF, REF_BATCH, BUDGET = 0.1, 6.0, 4, 100_000
-METHOD, BAN_IGNORE, POOL_IMAGES, GRID = "my_bvsb_predclsbal_pwr", False, 2975, "32x64"
-WORKLOAD = "configs[1]: my_bvsb_predclsbal_pwr acquisition round, synthetic Cityscapes-shaped pool"
 METRIC = "superpixel regions scored+selected/sec"
 UNIT = "regions/s"
+REL_TOL = 1e-5          # north_star: per-superpixel scores within 1e-5 relative (fp32)
 
 
-def use_voc_workload():
-    """BASELINE.json configs[2] (not the contract's default line): VOC-shaped pool, 10 582 images of 375x500 (native shape),
-    21 classes + the predicted-ignore channel, 150 superpixels, the _banignore selector, cls_weight_coeff 12, budget 10 000."""
-    global H, W, C, NSEG, COEFF, BUDGET, METHOD, BAN_IGNORE, POOL_IMAGES, GRID, WORKLOAD
-    H, W, C, NSEG, COEFF, BUDGET = 375, 500, 22, 150, 12.0, 10_000
-    METHOD, BAN_IGNORE, POOL_IMAGES, GRID = "my_bvsb_predclsbal_pwr_banignore", True, 10582, "10x15"
-    WORKLOAD = "configs[2]: my_bvsb_predclsbal_pwr_banignore acquisition round, synthetic PASCAL-VOC-shaped pool"
+@dataclasses.dataclass(frozen=True)
+class Workload:
+    """One acquisition configuration of BASELINE.json (shape, selector, budget)."""
+    key: str
+    label: str
+    H: int
+    W: int
+    C: int
+    nseg: int
+    coeff: float
+    budget: int
+    method: str
+    ban_ignore: bool
+    pool_images: int
+    grid: str
+    dtype: str = "f32"
+    temp: float = 0.1
+    ref_batch: int = 4
+
+    @property
+    def pixels(self):
+        return self.H * self.W
+
+    @property
+    def elt(self):
+        return 4 if self.dtype == "f32" else 2
+
+    @property
+    def bytes_per_image(self):
+        """P * (C' * sL + sI) read + the (S, C') {sum, count} tables written."""
+        return self.pixels * (self.C * self.elt + 4) + self.nseg * self.C * 8
+
+    def images_per_gpu(self):
+        return (self.pool_images + 7) // 8
+
+
+CITY = Workload("cityscapes", "configs[1]: my_bvsb_predclsbal_pwr acquisition round, synthetic Cityscapes-shaped pool",
+                1024, 2048, 19, 2048, 6.0, 100_000, "my_bvsb_predclsbal_pwr", False, 2975, "32x64")
+CITY_BF16 = dataclasses.replace(CITY, key="cityscapes_bf16", dtype="bf16",
+                                label="configs[1] with bf16 logits (north_star: stream bf16/fp32 logits)")
+VOC = Workload("voc", "configs[2]: my_bvsb_predclsbal_pwr_banignore acquisition round, synthetic PASCAL-VOC-shaped pool, native 375x500",
+               375, 500, 22, 150, 12.0, 10_000, "my_bvsb_predclsbal_pwr_banignore", True, 10582, "10x15")
+VOC_CROP = dataclasses.replace(VOC, key="voc_crop513", H=513, W=513,
+                               label="configs[2] at the reference's own pool shape: 513x513 resize+center-crop (rows not 16-byte aligned)")
+WORKLOADS = {w.key: w for w in (CITY, CITY_BF16, VOC, VOC_CROP)}
 
 
 def parse():
@@ -55,16 +102,20 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cityscapes", choices=["cityscapes", "voc"],
-                    help="cityscapes = BASELINE configs[1] (the contract line); voc = configs[2], 1323 images per GPU")
+    ap.add_argument("--workload", default="cityscapes", choices=sorted(WORKLOADS),
+                    help="headline workload of the line; cityscapes = BASELINE configs[1] (the contract line)")
     ap.add_argument("--images-per-gpu", type=int, default=0, help="0 = pool / 8 rounded up (372 Cityscapes, 1323 VOC)")
     ap.add_argument("--e2e-images", type=int, default=24, help="images per GPU in the host-buffer (e2e) step")
     ap.add_argument("--cpu-images", type=int, default=128, help="images in the bounded CPU-baseline sample (16 distinct images, cycled)")
+    ap.add_argument("--parity-images", type=int, default=16, help="images of the shard re-scored by the CPU port for the parity block")
     ap.add_argument("--coherent", type=int, default=0, help="draw logits at 1/k resolution and up-sample (0 = i.i.d.)")
     ap.add_argument("--lanes", type=int, default=2, help="side streams the scorer launches alternate over (1 = caller's stream only)")
     ap.add_argument("--group-mb", type=int, default=1536, help="logits queued per scorer launch (MB; 0 = one launch per batch of 4)")
+    ap.add_argument("--secondary", default="all", help="comma list of secondary entries (voc,voc_crop513,cityscapes_bf16,losses,labeller), 'all' or 'none'")
+    ap.add_argument("--secondary-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     return ap.parse_args()
 
 
@@ -76,10 +127,10 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def scorer_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the scorer, from the committed ncu --set full capture
-    of the same configuration (12 images x 19 x 1024 x 2048 f32 per grouped launch); None if the summary is missing."""
-    path = os.path.join(ROOT, "profiles", "r1_v7_scorer_tma_c19_12img_full.txt")
+def committed_traffic(name: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed ncu --set full capture
+    of the same configuration (profiles/<name>); None if the summary is missing."""
+    path = os.path.join(ROOT, "profiles", name)
     try:
         with open(path) as f:
             vals = [int(line.split()[-1]) for line in f if line.startswith("traffic = dram read + write")]
@@ -134,70 +185,85 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "interval_ms": 25}
 
 
-# ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_inputs(n_img: int, seed: int = 0):
+# ------------------------------------------------------------------------------------------------ CPU port (oracle)
+CPU_DISTINCT = 16   # distinct synthetic images held in host memory (2.7 GB Cityscapes); larger samples cycle through them
+
+
+def cpu_inputs(wl: Workload, n_img: int, seed: int = 0):
     from mulactseg_b200 import synth
-    return (synth.logits(n_img, C, H, W, "cosine", seed=seed), synth.superpixel_map(n_img, H, W, NSEG, "jitter", seed=seed + 1))
+    x = synth.logits(n_img, wl.C, wl.H, wl.W, "cosine", seed=seed)
+    if wl.dtype == "bf16":
+        x = x.to(torch.bfloat16).float()        # the CPU path has no bf16 kernels: fp32 arithmetic on the rounded values
+    return x, synth.superpixel_map(n_img, wl.H, wl.W, wl.nseg, "jitter", seed=seed + 1)
 
 
-CPU_DISTINCT = 16   # distinct synthetic images held in host memory (2.7 GB); larger samples cycle through them
+def synthetic_costs(n_regions: int) -> np.ndarray:
+    """Label cost (multi-hot class count, --fair_counting --or_labeling) of every region, indexed image * S + id."""
+    return np.random.RandomState(0).randint(1, 4, size=(n_regions,)).astype(np.int64)
 
 
-def cpu_round(n_img: int, seed: int = 0, inputs=None):
-    """The reference's CPU implementation of the path (oracle port: same torch ops, all host threads) on a
-    bounded sample of the workload: ``n_img`` pool images (batches of 4; beyond ``CPU_DISTINCT`` the same tensors
-    are fed again as further pool images -- every batch is still scored, ranked and selected from).
-    Returns (regions, seconds, phases)."""
+def cpu_round(wl: Workload, n_img: int, inputs, cost_all: np.ndarray, budget=None):
+    """The reference's CPU implementation of the path (oracle port: same torch ops, all host threads) on a bounded
+    sample of the workload: ``n_img`` pool images in batches of ``ref_batch`` (beyond the tensors in ``inputs`` the same
+    images are fed again as further pool images -- every batch is still scored, ranked and selected from).
+    -> dict(regions, seconds, phases, scores (n_img, S) f32, selected [(score, image, id)])."""
     from mulactseg_b200 import synth
     from oracle import acquisition as oa
-    logits, spx = inputs if inputs is not None else cpu_inputs(min(n_img, CPU_DISTINCT), seed)
+    logits, spx = inputs
     n_have = logits.shape[0]
-    im_idx, suppix = synth.pool_lists(n_img, NSEG)
-    rng = np.random.RandomState(seed)
-    cost = rng.randint(1, 4, size=(n_img, NSEG))
+    im_idx, suppix = synth.pool_lists(n_img, wl.nseg)
     index_of = {k[2]: i for i, k in enumerate(im_idx)}
     pool = []
-    for i in range(0, n_img, REF_BATCH):
+    for i in range(0, n_img, wl.ref_batch):
         j = i % n_have
-        m = min(REF_BATCH, n_img - i, n_have - j)
+        m = min(wl.ref_batch, n_img - i, n_have - j)
         pool.append((logits[j:j + m], spx[j:j + m]))
     n_img = sum(b[0].shape[0] for b in pool)
-    im_idx, cost = im_idx[:n_img], cost[:n_img]
+    im_idx = im_idx[:n_img]
+    cost = cost_all[: n_img * wl.nseg].reshape(n_img, wl.nseg)
     t0 = time.perf_counter()
-    scores = oa.scores_predclsbal_pwr(pool, NSEG, TEMP, COEFF, ban_ignore=BAN_IGNORE)
+    scores = oa.scores_predclsbal_pwr(pool, wl.nseg, wl.temp, wl.coeff, ban_ignore=wl.ban_ignore)
     t1 = time.perf_counter()
     ranked = oa.rank_regions(oa.score_list(im_idx, suppix, scores))
     t2 = time.perf_counter()
-    budget = max(1, int(BUDGET * n_img / POOL_IMAGES))
-    oa.expand_training_set(ranked, budget, [], {}, [list(k) for k in im_idx], {k: list(v) for k, v in suppix.items()},
-                           lambda p, s: cost[index_of[p], s])
+    if budget is None:
+        budget = max(1, int(wl.budget * n_img / wl.pool_images))
+    taken = oa.expand_training_set(ranked, budget, [], {}, [list(k) for k in im_idx], {k: list(v) for k, v in suppix.items()},
+                                   lambda p, s: cost[index_of[p], s])
     t3 = time.perf_counter()
-    return n_img * NSEG, t3 - t0, {"score_s": t1 - t0, "sort_s": t2 - t1, "select_s": t3 - t2}
+    path_index = {",".join(k): i for i, k in enumerate(im_idx)}
+    selected = [(s, path_index[p], i) for s, p, i in ranked[:taken]]
+    return {"regions": n_img * wl.nseg, "seconds": t3 - t0, "budget": budget, "scores": scores.numpy(), "selected": selected,
+            "phases": {"score_s": t1 - t0, "sort_s": t2 - t1, "select_s": t3 - t2}}
 
 
-def run_reference(args):
+def run_reference(args, wl: Workload):
+    """``--impl reference``: the reference's own CPU path for the same metric and config.  The reference is pure Python
+    over torch ops (+ torch_scatter, absent here) and cannot travel to the GPU box, so ``kind`` = "port": the oracle's
+    op-for-op restatement, all host threads, one loader batch of images per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    n_img = REF_BATCH   # one reference batch per step keeps the whole arm within a few minutes
-    inputs = cpu_inputs(n_img)
-    for _ in range(min(args.warmup, 1)):
-        cpu_round(n_img, inputs=inputs)
+    n_img = wl.ref_batch   # one reference batch per step keeps the whole arm within a few minutes
+    inputs = cpu_inputs(wl, n_img)
+    cost_all = synthetic_costs(n_img * wl.nseg)
+    for _ in range(args.warmup):
+        cpu_round(wl, n_img, inputs, cost_all)
     times, phases = [], None
-    for i in range(args.steps):
-        regions, sec, phases = cpu_round(n_img, inputs=inputs)
-        times.append(sec)
+    for _ in range(args.steps):
+        out = cpu_round(wl, n_img, inputs, cost_all)
+        times.append(out["seconds"]); phases = out["phases"]
     ms = 1e3 * float(np.mean(times))
-    value = n_img * NSEG / (ms / 1e3)
+    value = n_img * wl.nseg / (ms / 1e3)
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, n_img, note="CPU arm: each step is a bounded sample of the workload"),
+        "config": workload_config(args, wl, n_img, note="CPU arm: each step is a bounded sample of the workload (one loader batch)"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n_img} images of {H}x{W}x{C} per step (oracle port of the reference's torch ops: "
+                         "sample": f"{n_img} images of {wl.H}x{wl.W}x{wl.C} per step (oracle port of the reference's torch ops: "
                                    f"two passes, sorted(), expand_training_set); phases {json.dumps({k: round(v, 3) for k, v in phases.items()})}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -205,52 +271,189 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, images_per_gpu, note=""):
-    return {"workload": WORKLOAD,
-            "images_per_gpu": images_per_gpu, "height": H, "width": W, "classes": C, "nseg": NSEG,
-            "val_batch_size": REF_BATCH, "cls_weight_coeff": COEFF, "temperature": TEMP, "budget": BUDGET,
-            "fair_counting": True, "logits": "tanh(N(0,1))*0.9" + (f", coherent/{args.coherent}" if args.coherent else ", i.i.d."),
-            "superpixels": f"jittered {GRID} grid", "sharding": f"by image, dp{args.gpus}",
+def workload_config(args, wl: Workload, images_per_gpu, note=""):
+    return {"workload": wl.label, "images_per_gpu": images_per_gpu, "height": wl.H, "width": wl.W, "classes": wl.C, "nseg": wl.nseg,
+            "logits_dtype": wl.dtype, "val_batch_size": wl.ref_batch, "cls_weight_coeff": wl.coeff, "temperature": wl.temp,
+            "budget": wl.budget, "fair_counting": True,
+            "logits": "tanh(N(0,1))*0.9" + (f", coherent/{args.coherent}" if args.coherent else ", i.i.d."),
+            "superpixels": f"jittered {wl.grid} grid", "sharding": f"by image, dp{args.gpus}",
             "l2": "inputs (>= 4 GB per GPU) exceed the 126 MB L2; no flush needed", "note": note}
 
 
-# ------------------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
-    import torch.distributed as td
-    from mulactseg_b200 import _lib, acquisition as acq, selection, synth
+# ------------------------------------------------------------------------------------------------ GPU arm: acquisition
+class Ctx:
+    def __init__(self, args):
+        import torch.distributed as td
+        from mulactseg_b200 import _lib
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback in mulactseg_b200")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.td = td
+        if self.world > 1:
+            td.init_process_group("nccl", device_id=self.dev)
+        self.lib = _lib.load()
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback in mulactseg_b200")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        td.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
-    n_loc = args.images_per_gpu
-    n_tot = n_loc * world
-    P = H * W
-    spec = acq.SELECTORS[METHOD]
+    def sync_all(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.td.barrier()
+            torch.cuda.synchronize()
 
-    # ---- resident inputs (generated on the device, per chunk to bound temporaries)
-    logits = torch.empty((n_loc, C, H, W), dtype=torch.float32, device=dev)
-    spx = torch.empty((n_loc, H, W), dtype=torch.int32, device=dev)
-    chunk = 12
+    def max_over_ranks(self, x: float) -> float:
+        t = torch.tensor([x], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
+        return float(t.item())
+
+
+def make_inputs(ctx: Ctx, wl: Workload, n_loc: int):
+    """Resident inputs, generated on the device per chunk to bound temporaries."""
+    from mulactseg_b200 import synth
+    tdtype = torch.float32 if wl.dtype == "f32" else torch.bfloat16
+    logits = torch.empty((n_loc, wl.C, wl.H, wl.W), dtype=tdtype, device=ctx.dev)
+    spx = torch.empty((n_loc, wl.H, wl.W), dtype=torch.int32, device=ctx.dev)
+    chunk = max(1, (12 * 1024 * 2048) // wl.pixels)
     for i in range(0, n_loc, chunk):
         m = min(chunk, n_loc - i)
-        logits[i:i + m] = synth.logits(m, C, H, W, "cosine", seed=1000 * rank + i, device=dev, coherent=args.coherent)
-        spx[i:i + m] = synth.superpixel_map(m, H, W, NSEG, "jitter", seed=7000 * rank + i, device=dev, dtype=torch.int32)
-    # pool bookkeeping inputs: every region in the pool, image rank = global index, synthetic label costs
-    in_pool = torch.ones((n_loc, NSEG), dtype=torch.uint8, device=dev)
+        logits[i:i + m] = synth.logits(m, wl.C, wl.H, wl.W, "cosine", seed=1000 * ctx.rank + i, device=ctx.dev,
+                                       coherent=ctx.args.coherent).to(tdtype)
+        spx[i:i + m] = synth.superpixel_map(m, wl.H, wl.W, wl.nseg, "jitter", seed=7000 * ctx.rank + i, device=ctx.dev,
+                                            dtype=torch.int32)
+    return logits, spx
+
+
+def compare_with_cpu(wl: Workload, gpu_scores: np.ndarray, gpu_keys: np.ndarray, cpu: dict, tie_free_regions=None):
+    """GPU mini-round vs the CPU port on the same images: per-region scores within 1e-5 relative, selected region set
+    equal wherever score gaps exceed the tolerance (north_star).  -> parity dict (``ok`` = both hold)."""
+    ref = cpu["scores"].astype(np.float64).reshape(-1)
+    got = gpu_scores.astype(np.float64).reshape(-1)
+    keep = np.ones(ref.shape, dtype=bool) if tie_free_regions is None else tie_free_regions.reshape(-1)
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-30)
+    err[(ref == 0) & (got == 0)] = 0.0
+    max_err = float(err[keep].max()) if keep.any() else 0.0
+    gpu_sel = [int(k & np.uint64(0xFFFFFFFF)) for k in gpu_keys]
+    cpu_sel = [img * wl.nseg + sid for _, img, sid in cpu["selected"]]
+    cut = cpu["selected"][-1][0] if cpu["selected"] else 0.0
+    tol = REL_TOL * max(abs(cut), 1e-30)
+    score_of = lambda tie: ref[tie]      # noqa: E731
+    outside = [t for t in set(gpu_sel) ^ set(cpu_sel) if abs(score_of(t) - cut) > tol and keep[t]]
+    order_swaps = sum(1 for a, b in zip(gpu_sel, cpu_sel) if a != b)
+    ok = max_err <= REL_TOL and not outside
+    return {"ok": bool(ok), "regions_compared": int(keep.sum()), "max_rel_err": max_err, "tolerance": REL_TOL,
+            "selected_gpu": len(gpu_sel), "selected_cpu": len(cpu_sel), "selected_sets_equal": set(gpu_sel) == set(cpu_sel),
+            "selected_outside_tolerance": len(outside), "positions_differing_by_near_tie": int(order_swaps)}
+
+
+def gpu_mini_round(ctx: Ctx, wl: Workload, logits, spx, cost_dev, budget, group, image_rank, shard_counts=None):
+    """One whole round over a few images through the same code path as the timed step.  -> (scores dev, host keys)."""
+    from mulactseg_b200 import acquisition as acq, selection
+    m = logits.shape[0]
+    stats = acq.RegionStats(m, wl.nseg, wl.C, ctx.dev, need_prob=True, lanes=ctx.args.lanes, group_bytes=ctx.args.group_mb << 20)
+    for i in range(0, m, wl.ref_batch):
+        stats.add_batch(i, logits[i:i + wl.ref_batch], spx[i:i + wl.ref_batch], wl.temp)
+    scores, _ = acq.finalize(stats, acq.SELECTORS[wl.method], wl.coeff, wl.ref_batch, group, shard_counts)
+    in_pool = torch.ones((m, wl.nseg), dtype=torch.uint8, device=ctx.dev)
+    keys = selection.top_regions(scores, in_pool, image_rank, budget + 1, group, cost_dev, budget)
+    return scores, keys
+
+
+def parity_single(ctx: Ctx, wl: Workload, logits, spx, cost_all, cost_dev):
+    """N = 1: the first images of the shard through the GPU path and through the CPU port; also returns the CPU result
+    so that the timed CPU baseline can reuse the host copies."""
+    m = min(ctx.args.parity_images, logits.shape[0])
+    m -= m % wl.ref_batch if m > wl.ref_batch else 0
+    budget = max(1, int(wl.budget * m / wl.pool_images))
+    rank_t = torch.arange(m, dtype=torch.int32, device=ctx.dev)
+    scores, keys = gpu_mini_round(ctx, wl, logits[:m], spx[:m], cost_dev, budget, None, rank_t)
+    host = (logits[:m].float().cpu(), spx[:m].long().cpu())
+    cpu = cpu_round(wl, m, host, cost_all, budget)
+    tie_free = None
+    if wl.dtype != "f32":
+        # bf16 rounding creates exact top-2 ties; the reference's topk order among equal probabilities is arbitrary, so
+        # regions holding such a pixel have no defined reference value and are left out (their number is reported)
+        top = host[0].topk(2, dim=1).values
+        tied = (top[:, 0] == top[:, 1]).reshape(m, -1)
+        dirty = torch.zeros((m, wl.nseg), dtype=torch.bool)
+        for i in range(m):
+            ids = host[1][i].reshape(-1)[tied[i]]
+            dirty[i, ids] = True
+        tie_free = (~dirty).numpy()
+    out = compare_with_cpu(wl, scores.cpu().numpy(), keys, cpu, tie_free)
+    out.update({"images": m, "budget": budget, "against": "oracle port of the reference's torch ops on the same images (host copies of the resident inputs)"})
+    if tie_free is not None:
+        out["regions_with_tied_pixels_excluded"] = int((~tie_free).sum())
+    return out, host, cpu
+
+
+def parity_multi(ctx: Ctx, wl: Workload, logits, spx, cost_dev, final_keys: np.ndarray):
+    """N > 1 (SCALE runs; the GPU test tier has one GPU): (1) every rank must end the timed rounds with the SAME ranked
+    key list -- a hash of it is all-gathered and compared; (2) a sharded mini-round (16 images over the ranks, NCCL
+    merge) must select what ONE rank selects from the gathered images."""
+    from mulactseg_b200 import dist as mdist
+    td, world, rank = ctx.td, ctx.world, ctx.rank
+    regions = (final_keys & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    digest = torch.tensor([len(final_keys), zlib.crc32(final_keys.tobytes()), zlib.crc32(regions.tobytes())],
+                          dtype=torch.int64, device=ctx.dev)
+    all_digests = torch.empty(world * 3, dtype=torch.int64, device=ctx.dev)
+    td.all_gather_into_tensor(all_digests, digest)
+    rows = all_digests.view(world, 3).cpu().numpy()
+    same = bool((rows == rows[0]).all())
+
+    m = max(1, 16 // world)
+    m_tot = m * world
+    budget = max(1, int(wl.budget * m_tot / wl.pool_images))
+    rank_t = torch.arange(rank * m, (rank + 1) * m, dtype=torch.int32, device=ctx.dev)
+    _, keys_dist = gpu_mini_round(ctx, wl, logits[:m], spx[:m], cost_dev, budget, None, rank_t, [m] * world)
+    all_logits = torch.empty((m_tot,) + tuple(logits.shape[1:]), dtype=logits.dtype, device=ctx.dev)
+    all_spx = torch.empty((m_tot,) + tuple(spx.shape[1:]), dtype=spx.dtype, device=ctx.dev)
+    td.all_gather_into_tensor(all_logits, logits[:m].contiguous())
+    td.all_gather_into_tensor(all_spx, spx[:m].contiguous())
+    scores_one, keys_one = gpu_mini_round(ctx, wl, all_logits, all_spx, cost_dev, budget, mdist.SINGLE,
+                                          torch.arange(m_tot, dtype=torch.int32, device=ctx.dev))
+    del all_logits, all_spx
+    ref = scores_one.cpu().numpy().astype(np.float64).reshape(-1)
+    sel_d = [int(k & np.uint64(0xFFFFFFFF)) for k in keys_dist]
+    sel_o = [int(k & np.uint64(0xFFFFFFFF)) for k in keys_one]
+    cut = ref[sel_o[-1]] if sel_o else 0.0
+    tol = REL_TOL * max(abs(cut), 1e-30)
+    outside = [t for t in set(sel_d) ^ set(sel_o) if abs(ref[t] - cut) > tol]
+
+    def bits_to_score(keys):
+        hi = (keys >> np.uint64(32)).astype(np.uint32)
+        bits = np.where(hi & np.uint32(0x80000000), hi & np.uint32(0x7FFFFFFF), ~hi).astype(np.uint32)
+        return bits.view(np.float32).astype(np.float64)
+
+    sd = dict(zip(sel_d, bits_to_score(keys_dist)))
+    worst = max((abs(sd[t] - ref[t]) / max(abs(ref[t]), 1e-30) for t in sel_d), default=0.0)
+    flag = torch.tensor([0 if (same and not outside and worst <= REL_TOL) else 1], dtype=torch.int64, device=ctx.dev)
+    td.all_reduce(flag, op=td.ReduceOp.MAX)
+    return {"ok": int(flag.item()) == 0, "ranks_agree_on_final_ranking": same, "final_ranking_digest": [int(v) for v in rows[0]],
+            "mini_round_images": m_tot, "mini_round_selected_sharded": len(sel_d), "mini_round_selected_one_rank": len(sel_o),
+            "mini_round_sets_equal": set(sel_d) == set(sel_o), "mini_round_outside_tolerance": len(outside),
+            "mini_round_max_rel_err": float(worst), "tolerance": REL_TOL,
+            "against": "the same kernels on ONE rank over the all-gathered images (single-process path) + cross-rank digest"}
+
+
+def run_acquisition(ctx: Ctx, wl: Workload, n_loc: int, steps: int, warmup: int, headline: bool):
+    """Time `steps` whole rounds over the resident shard; -> the measurement dict (JSON-line fields)."""
+    from mulactseg_b200 import _lib, acquisition as acq, selection
+    args, world, rank, dev, td = ctx.args, ctx.world, ctx.rank, ctx.dev, ctx.td
+    n_tot = n_loc * world
+    spec = acq.SELECTORS[wl.method]
+    logits, spx = make_inputs(ctx, wl, n_loc)
+    in_pool = torch.ones((n_loc, wl.nseg), dtype=torch.uint8, device=dev)
     image_rank = torch.arange(rank * n_loc, (rank + 1) * n_loc, dtype=torch.int32, device=dev)
-    cost_all = np.random.RandomState(0).randint(1, 4, size=(n_tot * NSEG,)).astype(np.int64)
+    cost_all = synthetic_costs(n_tot * wl.nseg)
     cost_dev = torch.from_numpy(cost_all.astype(np.uint8)).to(dev)      # label cost of every region, indexed like the key's low word
-    k_sel = BUDGET + 1
-    stats = acq.RegionStats(n_loc, NSEG, C, dev, need_prob=True, lanes=args.lanes, group_bytes=args.group_mb << 20)
-    ev_pairs = []
-    launches_seen = []
+    k_sel = wl.budget + 1
+    stats = acq.RegionStats(n_loc, wl.nseg, wl.C, dev, need_prob=True, lanes=args.lanes, group_bytes=args.group_mb << 20)
+    ev, launches_seen = [], []
+    last_keys = [None]
 
     def step(record_events: bool):
         stats.zero_()
@@ -258,30 +461,27 @@ def run_ours(args):
         # kernel's average launch duration is the span of the scoring phase (fork -> join, events on the caller's
         # stream) divided by the number of launches
         if record_events:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
             l0 = stats.launches
-        for i in range(0, n_loc, REF_BATCH):
-            stats.add_batch(i, logits[i:i + REF_BATCH], spx[i:i + REF_BATCH], TEMP)    # one call per loader batch, like the plugin
+        for i in range(0, n_loc, wl.ref_batch):
+            stats.add_batch(i, logits[i:i + wl.ref_batch], spx[i:i + wl.ref_batch], wl.temp)    # one call per loader batch, like the plugin
         if record_events:
             stats.join()
             e1.record()
-            ev_pairs.append((e0, e1))
             launches_seen.append(stats.launches - l0)
-        scores, _ = acq.finalize(stats, spec, COEFF, REF_BATCH, None, [n_loc] * world)
+        scores, _ = acq.finalize(stats, spec, wl.coeff, wl.ref_batch, None, [n_loc] * world)
         # ranked keys on the host (uint64, descending), already cut where expand_training_set stops
-        keys = selection.top_regions(scores, in_pool, image_rank, k_sel, None, cost_dev, BUDGET)
+        keys = selection.top_regions(scores, in_pool, image_rank, k_sel, None, cost_dev, wl.budget)
+        if record_events:
+            e2.record()
+            ev.append((e0, e1, e2))
+        last_keys[0] = keys
         return len(keys)
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            td.barrier()
-            torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         picked = step(False)
-    sync_all()
+    ctx.sync_all()
 
     def phases():
         """One extra, untimed round with a device sync after every phase: where a round's time goes (wall clock, ms)."""
@@ -295,104 +495,113 @@ def run_ours(args):
         stats.zero_()
         mark("zero_tables")
         t_enq = time.perf_counter()
-        for i in range(0, n_loc, REF_BATCH):
-            stats.add_batch(i, logits[i:i + REF_BATCH], spx[i:i + REF_BATCH], TEMP)
+        for i in range(0, n_loc, wl.ref_batch):
+            stats.add_batch(i, logits[i:i + wl.ref_batch], spx[i:i + wl.ref_batch], wl.temp)
         stats.join()
-        enqueue_ms = 1e3 * (time.perf_counter() - t_enq)          # host time to enqueue the 93 launches (no sync)
+        enqueue_ms = 1e3 * (time.perf_counter() - t_enq)          # host time to enqueue the launches (no sync)
         mark("score")
-        scores, _ = acq.finalize(stats, spec, COEFF, REF_BATCH, None, [n_loc] * world)
+        scores, _ = acq.finalize(stats, spec, wl.coeff, wl.ref_batch, None, [n_loc] * world)
         mark("class_weights+region_scores")
-        selection.top_regions(scores, in_pool, image_rank, k_sel, None, cost_dev, BUDGET)
+        selection.top_regions(scores, in_pool, image_rank, k_sel, None, cost_dev, wl.budget)
         mark("top_regions(select+sort+budget_cut+d2h)")
         out = {b[0]: round(1e3 * (b[1] - a[1]), 3) for a, b in zip(marks, marks[1:])}
         out["score_host_enqueue"] = round(enqueue_ms, 3)
         return out
 
-    sampler = ClockSampler(local) if rank == 0 else None     # comes up while the phase breakdown runs
+    sampler = ClockSampler(ctx.local) if (rank == 0 and headline) else None     # comes up while the phase breakdown runs
     phase_ms = phases() if world == 1 else None
     if sampler is not None:
         time.sleep(0.3)
-    sync_all()
-    launches0 = lib.mas_kernel_launches()
+    ctx.sync_all()
+    launches0 = ctx.lib.mas_kernel_launches()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.cudart().cudaProfilerStart()   # no-op unless run under `ncu --profile-from-start off`
     wall0 = time.perf_counter()
     clock_t0 = time.time()
     t_start.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         picked = step(True)
     t_end.record()
-    sync_all()
+    ctx.sync_all()
     wall = time.perf_counter() - wall0
     clock_t1 = time.time()
     torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.stop(clock_t0, clock_t1) if sampler else None
-    launches = lib.mas_kernel_launches() - launches0
-    ms_total = torch.tensor([max(t_start.elapsed_time(t_end), 0.0)], device=dev, dtype=torch.float64)
-    if world > 1:
-        td.all_reduce(ms_total, op=td.ReduceOp.MAX)
-    ms_step = float(ms_total.item()) / args.steps
-    value = n_tot * NSEG / (ms_step / 1e3)
+    launches = ctx.lib.mas_kernel_launches() - launches0
+    ms_step = ctx.max_over_ranks(max(t_start.elapsed_time(t_end), 0.0)) / steps
+    value = n_tot * wl.nseg / (ms_step / 1e3)
 
     # dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events on the launch stream)
-    bytes_per_img = P * (C * 4 + 4) + NSEG * C * 8
-    dur = np.array([a.elapsed_time(b) for a, b in ev_pairs])            # scoring phase of each timed step, ms
+    dur = np.array([a.elapsed_time(b) for a, b, _ in ev])            # scoring phase of each timed step, ms
+    tail = np.array([b.elapsed_time(c) for _, b, c in ev])           # class weights .. winners on the host, ms
     n_launch = int(launches_seen[0])
-    bytes_per_launch = bytes_per_img * n_loc / n_launch
+    bytes_per_launch = wl.bytes_per_image * n_loc / n_launch
     launch_ms = float(np.mean(dur)) / n_launch
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
     peak, peak_src = peaks()
+    vec = "tma" if (wl.W * wl.elt) % 16 == 0 else ("ldg128+peel" if os.environ.get("MAS_SCORER_PEEL", "1") != "0" else "ldg32")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": scorer_traffic() if args.workload == "cityscapes" else None, "kernel": f"bvsb_stats_tma_kernel<{C},f32,prob>",
-                "peak_source": peak_src + ", sustained copy (the kernel runs back to back for the whole phase)",
+                "traffic": committed_traffic("r1_v7_scorer_tma_c19_12img_full.txt") if wl.key == "cityscapes" else None,
+                "kernel": f"bvsb_stats_{vec}_kernel<{wl.C},{wl.dtype},prob>",
+                "peak_source": peak_src + ", burst copy figure; the kernel runs back to back for the whole phase (see sustained_copy_GBps_this_box)",
                 "bytes_per_launch": int(bytes_per_launch), "mean_launch_ms": launch_ms, "launches_per_step": n_launch,
                 "lanes": args.lanes, "images_per_launch": round(n_loc / n_launch, 2),
-                "grouping": f"add_batch per loader batch of {REF_BATCH}; a launch covers the batches queued until {args.group_mb} MB "
+                "grouping": f"add_batch per loader batch of {wl.ref_batch}; a launch covers the batches queued until {args.group_mb} MB "
                             "of logits wait (<= 8 batches)",
                 "how": "span of the scoring phase (CUDA events on the caller's stream, fork -> join) / launches",
                 "kernel_share_of_step": float(dur.mean() / ms_step),
                 "scoring_phase_ms_per_step": [round(float(x), 3) for x in dur]}
-
-    # context for the roofline: the same STREAM-style copy MEASURED_PEAKS.json was made with, but held for ~0.4 s like the
-    # timed region (the scorer runs back to back under the 1000 W power cap, where clocks settle below the burst figure)
-    src = logits[:8].view(-1)
-    dst = torch.empty_like(src)
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 120
-    for _ in range(10):
-        dst.copy_(src)
-    c0.record()
-    for _ in range(reps):
-        dst.copy_(src)
-    c1.record()
-    torch.cuda.synchronize()
-    roofline["sustained_copy_GBps_this_box"] = round(2 * src.numel() * 4 * reps / (c0.elapsed_time(c1) * 1e-3) / 1e9, 1)
-    roofline["frac_of_sustained_copy"] = round(achieved / roofline["sustained_copy_GBps_this_box"], 4)
-    del dst
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
+           "data": "synthetic", "config": workload_config(args, wl, n_loc), "roofline": roofline,
+           "tail_ms_per_step": {"mean": round(float(tail.mean()), 4), "max_over_steps": round(float(tail.max()), 4),
+                                "what": "class weights (+ all-gather), region scores, candidate select (+ all-gather of the messages), "
+                                        "merge + sort, budget cut, winners to the host; CUDA events, this rank"},
+           "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * wall / steps, "selected_regions": int(picked)}
+    if headline:
+        out["clocks"] = clocks
+        out["phases_ms_synced"] = phase_ms
+        # context for the roofline: the same STREAM-style copy MEASURED_PEAKS.json was made with, but held for ~0.4 s like the
+        # timed region (the scorer runs back to back under the 1000 W power cap, where clocks settle below the burst figure)
+        src = logits[:8].view(-1)
+        dst = torch.empty_like(src)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 120
+        for _ in range(10):
+            dst.copy_(src)
+        c0.record()
+        for _ in range(reps):
+            dst.copy_(src)
+        c1.record()
+        torch.cuda.synchronize()
+        roofline["sustained_copy_GBps_this_box"] = round(2 * src.numel() * src.element_size() * reps / (c0.elapsed_time(c1) * 1e-3) / 1e9, 1)
+        roofline["frac_of_sustained_copy"] = round(achieved / roofline["sustained_copy_GBps_this_box"], 4)
+        del dst
 
     # ---- end-to-end through the C ABI with HOST buffers (H2D of logits + ids inside the timed region)
-    e2e = None
-    if not args.no_e2e:
+    if headline and not args.no_e2e:
         n_e = min(args.e2e_images, n_loc)
-        h_logits = torch.empty((n_e, C, H, W), dtype=torch.float32).pin_memory()
-        h_spx = torch.empty((n_e, H, W), dtype=torch.int32).pin_memory()
+        h_logits = torch.empty((n_e, wl.C, wl.H, wl.W), dtype=logits.dtype).pin_memory()
+        h_spx = torch.empty((n_e, wl.H, wl.W), dtype=torch.int32).pin_memory()
         h_logits.copy_(logits[:n_e]); h_spx.copy_(spx[:n_e])
         torch.cuda.synchronize()
-        h_score = np.empty(n_e * NSEG, dtype=np.float32)
-        h_pool = np.ones(n_e * NSEG, dtype=np.uint8)
+        h_score = np.empty(n_e * wl.nseg, dtype=np.float32)
+        h_pool = np.ones(n_e * wl.nseg, dtype=np.uint8)
         h_rank = np.arange(n_e, dtype=np.int32)
-        k_e = min(int(BUDGET * n_e / n_loc / 8) + 1, n_e * NSEG)
+        k_e = min(int(wl.budget * n_e / n_loc / 8) + 1, n_e * wl.nseg)
         h_keys = np.zeros(k_e, dtype=np.uint64)
         h_cnt = np.zeros(1, dtype=np.int32)
 
         def e2e_step():
-            _lib.call("mas_acquisition_host", h_logits.data_ptr(), 0, h_spx.data_ptr(), n_e, C, H, W, NSEG, TEMP, 1, COEFF,
-                      REF_BATCH, 0, C - 1 if BAN_IGNORE else -1, 0, REF_BATCH, h_score.ctypes.data, None, None)
-            _lib.call("mas_select_topk_host", h_score.ctypes.data, h_pool.ctypes.data, h_rank.ctypes.data, n_e, NSEG, k_e,
+            _lib.call("mas_acquisition_host", h_logits.data_ptr(), _lib.MAS_F32 if wl.dtype == "f32" else _lib.MAS_BF16,
+                      h_spx.data_ptr(), n_e, wl.C, wl.H, wl.W, wl.nseg, wl.temp, 1, wl.coeff,
+                      wl.ref_batch, 0, wl.C - 1 if wl.ban_ignore else -1, 0, wl.ref_batch, h_score.ctypes.data, None, None)
+            _lib.call("mas_select_topk_host", h_score.ctypes.data, h_pool.ctypes.data, h_rank.ctypes.data, n_e, wl.nseg, k_e,
                       h_keys.ctypes.data, h_cnt.ctypes.data)
             return selection.cumulative_cut(cost_all[(h_keys[: int(h_cnt[0])] & np.uint64(0xFFFFFFFF)).astype(np.int64)], k_e - 1)
 
-        # plain pinned-host -> device copy of the same buffers: the PCIe ceiling of this box for the e2e step
+        # plain pinned-host -> device copy of the same buffers, alone on the bus: a reference point for the e2e step
+        # (not a bound under --gpus N, where the ranks' steps contend for the host's PCIe complex differently than this probe)
         stage = torch.empty_like(logits[:n_e])
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stage.copy_(h_logits, non_blocking=True)
@@ -400,55 +609,246 @@ def run_ours(args):
         stage.copy_(h_logits, non_blocking=True)
         c1.record()
         torch.cuda.synchronize()
-        h2d_gbps = h_logits.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        h2d_gbps = h_logits.numel() * h_logits.element_size() / (c0.elapsed_time(c1) * 1e-3) / 1e9
         del stage
         e2e_step()
-        sync_all()
-        n_rep = max(2, min(args.steps, 5))
+        ctx.sync_all()
+        n_rep = max(2, min(steps, 5))
         t0 = time.perf_counter()
         for _ in range(n_rep):
             e2e_step()
-        sync_all()
-        sec = torch.tensor([(time.perf_counter() - t0) / n_rep], device=dev, dtype=torch.float64)
-        if world > 1:
-            td.all_reduce(sec, op=td.ReduceOp.MAX)
-        e2e = {"value": world * n_e * NSEG / float(sec.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(n_e * P * (C * 4 + 4) + n_e * NSEG * 5 + n_e * 4),
-               "d2h_bytes_per_step": int(n_e * NSEG * 4 + k_e * 8 + 4),
-               "images_per_gpu": n_e, "ms_per_step": 1e3 * float(sec.item()), "h2d_copy_GBps_this_box": round(h2d_gbps, 1),
-               "h2d_floor_ms": round(1e3 * (n_e * P * (C * 4 + 4)) / (h2d_gbps * 1e9), 1),
-               "api": "mas_acquisition_host + mas_select_topk_host (C ABI, pinned host buffers, chunked double-buffered H2D)"}
+        ctx.sync_all()
+        sec = ctx.max_over_ranks((time.perf_counter() - t0) / n_rep)
+        out["e2e"] = {"value": world * n_e * wl.nseg / sec, "unit": UNIT,
+                      "h2d_bytes_per_step": int(n_e * wl.pixels * (wl.C * wl.elt + 4) + n_e * wl.nseg * 5 + n_e * 4),
+                      "d2h_bytes_per_step": int(n_e * wl.nseg * 4 + k_e * 8 + 4),
+                      "images_per_gpu": n_e, "ms_per_step": 1e3 * sec, "h2d_copy_GBps_this_box": round(h2d_gbps, 1),
+                      "h2d_probe_ms": round(1e3 * (n_e * wl.pixels * (wl.C * wl.elt + 4)) / (h2d_gbps * 1e9), 1),
+                      "api": "mas_acquisition_host + mas_select_topk_host (C ABI, pinned host buffers, chunked double-buffered H2D)"}
+        del h_logits, h_spx
+    elif headline:
+        out["e2e"] = None
 
+    # ---- parity inside the run, and the CPU baseline on the same host copies
+    parity, host, cpu_small = None, None, None
+    if not args.no_parity:
+        if world == 1:
+            parity, host, cpu_small = parity_single(ctx, wl, logits, spx, cost_all, cost_dev)
+        else:
+            parity = parity_multi(ctx, wl, logits, spx, cost_dev, last_keys[0])
+    out["parity"] = parity
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        n_c = max(REF_BATCH, args.cpu_images)
-        regions, sec, phases = cpu_round(n_c)
-        cpu = {"value": regions / sec, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{regions // NSEG} of the {n_loc} images ({regions} regions; {CPU_DISTINCT} distinct, cycled) in {sec:.1f} s: "
-                         f"{json.dumps({k: round(v, 2) for k, v in phases.items()})}"}
+        if host is None:
+            m = min(CPU_DISTINCT, n_loc)
+            host = (logits[:m].float().cpu(), spx[:m].long().cpu())
+        n_c = max(wl.ref_batch, args.cpu_images if headline else min(args.cpu_images, 64))
+        if wl.pixels < 1024 * 2048:
+            n_c = n_c * 4                 # small images: keep the sample at seconds of CPU work
+        res = cpu_round(wl, n_c, host, synthetic_costs(n_c * wl.nseg))
+        cpu = {"value": res["regions"] / res["seconds"], "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{res['regions'] // wl.nseg} pool images ({res['regions']} regions; the first {host[0].shape[0]} images of the shard, "
+                         f"cycled) in {res['seconds']:.1f} s: {json.dumps({k: round(v, 2) for k, v in res['phases'].items()})}"}
+    out["cpu_baseline"] = cpu
+    del logits, spx, stats
+    torch.cuda.empty_cache()
+    return out
 
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": workload_config(args, n_loc), "roofline": roofline, "cpu_baseline": cpu,
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "phases_ms_synced": phase_ms, "wall_ms_per_step": 1e3 * wall / args.steps,
-                "selected_regions": int(picked)}
+
+# ------------------------------------------------------------------------------------------------ secondary: losses, labeller
+def time_ms(fn, warmup=3, iters=10):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def run_losses(ctx: Ctx, rho: float, steps: int):
+    """BASELINE configs[3]: stage-1 multi-hot partial-label + MIL loss step (fwd + bwd) on batch-16 logits of 768x768 train
+    crops, 20 channels, 2048 superpixels + pad id, int64 ids, T = 0.1, trainer coefficients 16 / 8 / 1."""
+    from mulactseg_b200 import losses, synth
+    from oracle import losses as olo
+    dev = ctx.dev
+    n, c, h, w, nseg = 16, 20, 768, 768, 2048
+    x = synth.logits(n, c, h, w, "cosine", seed=1, device=dev, coherent=4)
+    spx = synth.pad_border(synth.superpixel_map(n, h, w, nseg, "jitter", seed=2, device=dev), nseg, 16)
+    trg = synth.multihot_targets(n, nseg, c, seed=3, device=dev, p_ignore=0.0)
+    mask = synth.region_mask(spx, nseg, rho, seed=4)
+    a = types.SimpleNamespace(nseg=nseg, group_ce_temp=0.1, multi_ce_temp=0.1)
+    group, multi = losses.stage1_criterion(a, c - 1)
+    xs = [x.clone().requires_grad_(True) for _ in range(3)]   # a fresh `preds` every step, like net(images); 3 x 755 MB > L2
+    turn = [0]
+
+    def total(xin, t, s, m):
+        g = group(xin, t, s, m)
+        ce, mc = multi(xin, t, s, m)
+        return 16.0 * ce + 8.0 * mc + g, (ce, mc, g)
+
+    def step():
+        turn[0] += 1
+        xin = xs[turn[0] % len(xs)]
+        xin.grad = None
+        total(xin, trg, spx, mask)[0].backward()
+
+    launches0 = ctx.lib.mas_kernel_launches()
+    ms = time_ms(step, iters=max(steps, 5))
+    launches = (ctx.lib.mas_kernel_launches() - launches0) // (3 + max(steps, 5))
+    frac = float(mask.float().mean())
+    P = h * w
+    # algorithmic bytes (SURVEY 8d): mask + int64 ids both directions, logits where selected (fwd + bwd), dense grad
+    alg = n * P * ((1 + 8) * 2 + frac * c * 4 * 2 + c * 4)
+    peak, _ = peaks()
+    out = {"workload": f"configs[3]: stage-1 loss step fwd+bwd, N=16 x 20 x 768 x 768, 2048 superpixels + pad id, labelled fraction rho={rho}",
+           "metric": "train crops/s through the fused loss step (fwd+bwd)", "unit": "crops/s", "value": n / (ms / 1e3), "ms": ms,
+           "selected_frac": round(frac, 4), "alg_bytes": int(alg), "launches_per_step": int(launches),
+           "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / ms / 1e6 / peak,
+                        "how": "algorithmic bytes of the whole step / CUDA-event time of the whole step (kernels + glue + host gaps)"}}
+    if ctx.args.no_cpu_baseline:
+        return out
+    # CPU port on a bounded sample (the first 2 crops) -- and the parity of the GPU step on exactly those crops
+    m = 2
+    torch.set_num_threads(os.cpu_count() or 1)
+    xc, tc, sc, mc_ = x[:m].cpu(), trg[:m].cpu(), spx[:m].cpu(), mask[:m].cpu()
+    xr = xc.clone().requires_grad_(True)
+    t0 = time.perf_counter()
+    ref_total, ref_parts = olo.stage1_total(xr, tc, sc, mc_, nseg, 0.1, 0.1)
+    ref_total.backward()
+    sec = time.perf_counter() - t0
+    xg = x[:m].clone().requires_grad_(True)
+    got_total, got_parts = total(xg, trg[:m].contiguous(), spx[:m].contiguous(), mask[:m].contiguous())
+    got_total.backward()
+    torch.cuda.synchronize()
+    ref_grad, got_grad = xr.grad.numpy(), xg.grad.cpu().numpy()
+    val_err = max(abs(float(g) - float(r)) / max(abs(float(r)), 1e-30) for g, r in zip(got_parts, ref_parts))
+    grad_err = float(np.max(np.abs(got_grad - ref_grad)) / max(float(np.abs(ref_grad).max()), 1e-30))
+    out["cpu_baseline"] = {"value": m / sec, "unit": "crops/s", "cores": torch.get_num_threads(), "kind": "port",
+                           "sample": f"{m} of the 16 crops, oracle port fwd+bwd (autograd) in {sec:.1f} s"}
+    out["parity"] = {"ok": bool(val_err <= REL_TOL and grad_err <= 1e-4), "loss_max_rel_err": val_err, "tolerance": REL_TOL,
+                     "grad_max_abs_err_over_max_grad": grad_err, "grad_tolerance": 1e-4, "crops": m,
+                     "against": "oracle port (torch autograd on the CPU) on the same crops"}
+    return out
+
+
+def run_labeller(ctx: Ctx, name: str, steps: int):
+    """BASELINE configs[4]: stage-2 prototype pseudo-labelling of one image (includeonehot, median threshold), 256-d features."""
+    from mulactseg_b200 import labeller, synth
+    from oracle import labeller as ol
+    dev = ctx.dev
+    h, w, nseg, c, rho = {"cityscapes": (1024, 2048, 2048, 20, 0.08), "voc": (375, 500, 150, 21, 0.3)}[name]
+    n_rot = 4 if name == "cityscapes" else 16          # rotate over several images: 4 x 2.3 GB / 16 x 0.2 GB, beyond L2
+    feats = [synth.features(1, 256, h, w, seed=10 + i, device=dev) for i in range(n_rot)]
+    logits = [synth.logits(1, c, h, w, "normal", seed=30 + i, device=dev, coherent=4) for i in range(n_rot)]
+    spx = synth.superpixel_map(1, h, w, nseg, "jitter", seed=3, device=dev)
+    trg = synth.multihot_targets(1, nseg, c, seed=4, device=dev, p_ignore=0.0)
+    mask = synth.region_mask(spx, nseg, rho, seed=5)
+    turn = [0]
+
+    def step():
+        turn[0] += 1
+        i = turn[0] % n_rot
+        return labeller.pseudo_label_generation(None, feats[i], logits[i], trg, mask, spx, check=False)
+
+    launches0 = ctx.lib.mas_kernel_launches()
+    ms = time_ms(step, iters=max(steps, 5) * 2)
+    launches = (ctx.lib.mas_kernel_launches() - launches0) // (3 + max(steps, 5) * 2)
+    out_lab = labeller.pseudo_label_generation(None, feats[0], logits[0], trg, mask, spx)
+    sel = float(mask.float().mean())
+    P = h * w
+    # feature columns of selected pixels (assign) + of every unselected pixel of a touched superpixel (propagate, once)
+    chosen = torch.zeros(nseg, dtype=torch.bool, device=dev)
+    chosen[spx[0][mask[0]]] = True
+    near = torch.nn.functional.max_pool2d(chosen[spx[0]].float()[None, None], 3, 1, 1)[0, 0] > 0
+    touched = torch.zeros(nseg, dtype=torch.bool, device=dev)
+    touched[spx[0][near]] = True
+    touched_frac = float(touched[spx[0]].float().mean())
+    alg = P * (1 + 8) * 3 + sel * P * c * 4 + touched_frac * P * 256 * 4 + P
+    peak, _ = peaks()
+    out = {"workload": f"configs[4]: cosplbl_prop prototype labeller, one {h}x{w} image, 256-d features, {c} classes, {nseg} superpixels, rho={rho}",
+           "metric": "images/s through pseudo_label_generation", "unit": "images/s", "value": 1e3 / ms, "ms": ms,
+           "selected_frac": round(sel, 4), "touched_frac": round(touched_frac, 4), "labelled_frac": round(float((out_lab != 255).float().mean()), 4),
+           "alg_bytes": int(alg), "launches_per_image": int(launches),
+           "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / ms / 1e6 / peak,
+                        "how": "algorithmic bytes of one image / CUDA-event time per image (all kernels + glue)"}}
+    if ctx.args.no_cpu_baseline:
+        return out
+    torch.set_num_threads(os.cpu_count() or 1)
+    cpu_in = (feats[0].cpu(), logits[0].cpu(), trg.cpu(), mask.cpu(), spx.cpu())
+    t0 = time.perf_counter()
+    ref = ol.pseudo_label_generation(*cpu_in)
+    sec = time.perf_counter() - t0
+    differ = int((out_lab.cpu() != ref).sum())
+    out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                           "sample": f"the same image, oracle port (own-superpixel + adjacent blocks only, i.e. far less work than the "
+                                     f"reference's dense mm + CPU dilation loop) in {sec:.1f} s"}
+    out["parity"] = {"ok": differ <= 2, "pixels": P, "pixels_differing": differ, "against": "oracle port on the same image (labels are integers)"}
+    return out
+
+
+def secondary_entry(res: dict) -> dict:
+    """Trim an acquisition measurement to a secondary entry."""
+    keep = ("metric", "value", "unit", "ms_per_step", "dtype", "roofline", "tail_ms_per_step", "cpu_baseline", "parity", "gpu_launches",
+            "selected_regions")
+    out = {"workload": res["config"]["workload"], "images_per_gpu": res["config"]["images_per_gpu"],
+           "shape": [res["config"]["classes"], res["config"]["height"], res["config"]["width"]], "nseg": res["config"]["nseg"]}
+    out.update({k: res[k] for k in keep if k in res})
+    out["ms"] = out.pop("ms_per_step")
+    out["alg_bytes"] = int(res["roofline"]["bytes_per_launch"] * res["roofline"]["launches_per_step"])
+    return out
+
+
+def run_ours(args, wl: Workload):
+    ctx = Ctx(args)
+    n_loc = args.images_per_gpu or wl.images_per_gpu()
+    line = run_acquisition(ctx, wl, n_loc, args.steps, args.warmup, headline=True)
+    wanted = [] if args.secondary == "none" else (
+        ["voc", "voc_crop513", "cityscapes_bf16", "losses", "labeller"] if args.secondary == "all" else args.secondary.split(","))
+    secondary = []
+    for name in wanted:
+        t0 = time.perf_counter()
+        try:
+            if name in WORKLOADS:
+                if name == wl.key:
+                    continue
+                w2 = WORKLOADS[name]
+                res = run_acquisition(ctx, w2, args.images_per_gpu or w2.images_per_gpu(), max(args.secondary_steps, 3), 3, headline=False)
+                entries = [secondary_entry(res)]
+            elif name == "losses" and ctx.world == 1:
+                entries = [run_losses(ctx, rho, args.secondary_steps) for rho in (0.02, 0.2, 1.0)]
+            elif name == "labeller" and ctx.world == 1:
+                entries = [run_labeller(ctx, which, args.secondary_steps) for which in ("cityscapes", "voc")]
+            else:
+                continue          # losses / labeller do not shard: one GPU (N = 1 line) is the measurement
+        except Exception as exc:      # a secondary entry never takes the headline down with it
+            entries = [{"workload": name, "error": f"{type(exc).__name__}: {exc}"}]
+        for e in entries:
+            e["bench_seconds"] = round((time.perf_counter() - t0) / len(entries), 1)
+        secondary.extend(entries)
+        torch.cuda.empty_cache()
+    line["secondary"] = secondary
+    ok = all((e.get("parity") or {}).get("ok", True) for e in [line] + secondary) and not any("error" in e for e in secondary)
+    if ctx.rank == 0:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        td.destroy_process_group()
+    if ctx.world > 1:
+        ctx.td.destroy_process_group()
+    if not ok:
+        print("bench.py: a parity check or a secondary entry FAILED (see the `parity` / `error` fields of the line)", file=sys.stderr)
+        raise SystemExit(1)
 
 
 def main():
     args = parse()
-    if args.workload == "voc":
-        use_voc_workload()
-    if args.images_per_gpu <= 0:
-        args.images_per_gpu = (POOL_IMAGES + 7) // 8
+    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, wl)
     else:
-        run_ours(args)
+        run_ours(args, wl)
 
 
 if __name__ == "__main__":

@@ -17,11 +17,20 @@ import torch
 import torch.distributed as td
 
 
+# pass as ``group`` to keep a call local to this process although torch.distributed is initialised (bench.py recomputes a
+# sharded mini-round on ONE rank this way to check the multi-GPU merge against it)
+SINGLE = "single-process"
+
+
 def is_distributed(group=None) -> bool:
+    if group is SINGLE:
+        return False
     return td.is_available() and td.is_initialized() and td.get_world_size(group) > 1
 
 
 def rank_world(group=None) -> Tuple[int, int]:
+    if group is SINGLE:
+        return 0, 1
     if td.is_available() and td.is_initialized():
         return td.get_rank(group), td.get_world_size(group)
     return 0, 1

@@ -398,8 +398,11 @@ _workspaces = {}
 
 
 def _labeller_workspace(device, fch, c, h, w, nseg) -> torch.Tensor:
+    """Scratch of the prototype labeller, cached per (device, stream): calls on different streams never share (or
+    regrow) a buffer that kernels queued on another stream still use."""
     need = int(_lib.load().mas_proto_labeller_workspace_bytes(fch, c, h, w, nseg))
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (index, torch._C._cuda_getCurrentRawStream(index))
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < need:
         buf = torch.empty(need, dtype=torch.uint8, device=device)   # caching-allocator blocks are >= 512-byte aligned

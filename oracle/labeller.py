@@ -24,8 +24,16 @@ from scipy import ndimage
 
 def neighbour_ids(spx_map: np.ndarray, sid: int) -> np.ndarray:
     """eval_save_cosplbl_prop.py:260-266 -- ids met inside the 3x3-dilated mask of ``sid`` (itself included)."""
-    grown = ndimage.binary_dilation(spx_map == sid, structure=np.ones((3, 3), np.uint8))
-    return np.unique(spx_map[grown])
+    own = spx_map == sid
+    ys, xs = np.nonzero(own)
+    if ys.size == 0:
+        return np.empty(0, dtype=spx_map.dtype)
+    # the dilation only reaches one pixel beyond the superpixel's bounding box: work on that window (same result as
+    # dilating the full-size mask, without a pass over the whole image per superpixel)
+    y0, y1 = max(int(ys.min()) - 1, 0), min(int(ys.max()) + 2, spx_map.shape[0])
+    x0, x1 = max(int(xs.min()) - 1, 0), min(int(xs.max()) + 2, spx_map.shape[1])
+    grown = ndimage.binary_dilation(own[y0:y1, x0:x1], structure=np.ones((3, 3), np.uint8))
+    return np.unique(spx_map[y0:y1, x0:x1][grown])
 
 
 def pseudo_label_image(feat: torch.Tensor, logits: torch.Tensor, target: torch.Tensor,
@@ -64,7 +72,9 @@ def pseudo_label_image(feat: torch.Tensor, logits: torch.Tensor, target: torch.T
         proto = fpix[pix[first]]                               # (K, Ch) feature at the arg-max-prob pixel
         sim = proto @ fpix[pix].T                              # (K, n_s)
         smax = sim.max(dim=0).values
-        kstar = torch.stack([(sim[:, j] == smax[j]).nonzero()[0, 0] for j in range(pix.numel())])
+        # first prototype index attaining the maximum, per pixel (vectorised `(sim[:, j] == smax[j]).nonzero()[0, 0]`)
+        rows = torch.arange(cls.numel()).view(-1, 1).expand_as(sim)
+        kstar = torch.where(sim == smax[None, :], rows, torch.full_like(rows, cls.numel())).min(dim=0).values
         own_label[where] = cls[kstar]
         thr = torch.ones(cls.numel())
         for k in range(cls.numel()):

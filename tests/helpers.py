@@ -63,3 +63,27 @@ def class_weights_ref(prob_sum_all, pixels_per_image, ref_batch, coeff):
         cumulated += (part.sum(dim=0) / (part.shape[0] * pixels_per_image)).to(torch.float32)
         n_batches += 1
     return (float(coeff) * (cumulated / n_batches) + 1.0) ** (-2)
+
+
+def tie_free(logits, temp, bump=0.01, dtype=None, drop_last_too=False):
+    """Remove exact top-2 ties so that the oracle is well defined: the reference takes ``topk`` on the softmax
+    PROBABILITIES (my_bvsb.py:20-21), whose order among equal values is arbitrary, while the kernels keep the first
+    index.  Pixels whose two largest probabilities are equal floats get their arg-max logit bumped; with ``dtype`` the
+    result stays exactly representable in it (bf16 inputs); ``drop_last_too``: also tie-free over the first C-1 planes
+    (the ``preds[:, :-1]`` view plain my_bvsb reads on predignore nets)."""
+    x = logits.float().clone()
+    for _ in range(8):
+        dirty = False
+        for view in ((x, x[:, :-1]) if drop_last_too else (x,)):
+            prob = torch.softmax(view / temp, dim=1)
+            top = prob.topk(2, dim=1)
+            tie = top.values[:, 0] == top.values[:, 1]
+            if bool(tie.any()):
+                dirty = True
+                first = view.argmax(dim=1, keepdim=True)
+                view.scatter_add_(1, first, tie.unsqueeze(1).to(view.dtype) * bump)     # in place: views write through to x
+        if dtype is not None:
+            x = x.to(dtype).float()
+        if not dirty:
+            return x
+    raise AssertionError("could not make the logits tie-free")

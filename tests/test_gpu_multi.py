@@ -66,8 +66,19 @@ def test_two_gpus_match_one(method, tmp_path):
     assert parts[0]["prefix"] == parts[1]["prefix"]                      # every rank ends with the same ranking
     got = [(p, i) for _, p, i in parts[0]["prefix"]]
     want = [(p, i) for _, p, i in prefix]
+    tol = 1e-5 * max(1.0, abs(prefix[0][0]))
     gaps = np.abs(np.diff([s for s, _, _ in prefix]))
-    if np.all(gaps > 1e-5 * max(1.0, abs(prefix[0][0]))):
+    if np.all(gaps > tol):
         assert got == want
-    else:                                                                # near-ties may swap neighbours
-        assert sorted(got[: k - 5]) == sorted(got[: k - 5]) and len(set(got) & set(want)) >= k - 3
+    else:
+        # near-ties may swap neighbours (fp32 atomics order the sums differently run to run): wherever the two rankings
+        # disagree, the scores at that position must agree within the tolerance, and the SETS may differ only in regions
+        # whose score is within the tolerance of the cut (the k-th score)
+        s_two = {(p, i): sc for sc, p, i in parts[0]["prefix"]}
+        s_one = {(p, i): sc for sc, p, i in prefix}
+        for a, b in zip(got, want):
+            if a != b:
+                assert abs(s_two[a] - s_one[b]) <= tol
+        cut = prefix[-1][0]
+        for region in set(got) ^ set(want):
+            assert abs((s_two.get(region, s_one.get(region))) - cut) <= tol
