@@ -327,12 +327,12 @@ def make_inputs(ctx: Ctx, wl: Workload, n_loc: int):
     return logits, spx
 
 
-def compare_with_cpu(wl: Workload, gpu_scores: np.ndarray, gpu_keys: np.ndarray, cpu: dict, tie_free_regions=None):
+def compare_with_cpu(wl: Workload, gpu_scores: np.ndarray, gpu_keys: np.ndarray, cpu: dict):
     """GPU mini-round vs the CPU port on the same images: per-region scores within 1e-5 relative, selected region set
     equal wherever score gaps exceed the tolerance (north_star).  -> parity dict (``ok`` = both hold)."""
     ref = cpu["scores"].astype(np.float64).reshape(-1)
     got = gpu_scores.astype(np.float64).reshape(-1)
-    keep = np.ones(ref.shape, dtype=bool) if tie_free_regions is None else tie_free_regions.reshape(-1)
+    keep = np.ones(ref.shape, dtype=bool)
     err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-30)
     err[(ref == 0) & (got == 0)] = 0.0
     max_err = float(err[keep].max()) if keep.any() else 0.0
@@ -362,6 +362,23 @@ def gpu_mini_round(ctx: Ctx, wl: Workload, logits, spx, cost_dev, budget, group,
     return scores, keys
 
 
+def tie_free_device(x: torch.Tensor, temp: float, bump: float = 0.02) -> torch.Tensor:
+    """bf16 rounding makes many pixels' two largest logits EQUAL; the reference takes topk on the probabilities, whose
+    order among equal values is arbitrary, so such pixels have no defined reference arg-max.  For the parity mini-round
+    the arg-max logit of tied pixels is bumped (and re-rounded to the input dtype) until no pixel ties: both the GPU path
+    and the CPU port then see the same, well-defined bf16 values."""
+    for _ in range(8):
+        xf = x.float()
+        top = torch.softmax(xf / temp, dim=1).topk(2, dim=1).values
+        tie = top[:, 0] == top[:, 1]
+        if not bool(tie.any()):
+            return x
+        first = xf.argmax(dim=1, keepdim=True)
+        xf.scatter_add_(1, first, tie.unsqueeze(1).float() * bump)
+        x = xf.to(x.dtype)
+    raise RuntimeError("could not make the parity sample tie-free")
+
+
 def parity_single(ctx: Ctx, wl: Workload, logits, spx, cost_all, cost_dev):
     """N = 1: the first images of the shard through the GPU path and through the CPU port; also returns the CPU result
     so that the timed CPU baseline can reuse the host copies."""
@@ -369,24 +386,17 @@ def parity_single(ctx: Ctx, wl: Workload, logits, spx, cost_all, cost_dev):
     m -= m % wl.ref_batch if m > wl.ref_batch else 0
     budget = max(1, int(wl.budget * m / wl.pool_images))
     rank_t = torch.arange(m, dtype=torch.int32, device=ctx.dev)
-    scores, keys = gpu_mini_round(ctx, wl, logits[:m], spx[:m], cost_dev, budget, None, rank_t)
-    host = (logits[:m].float().cpu(), spx[:m].long().cpu())
-    cpu = cpu_round(wl, m, host, cost_all, budget)
-    tie_free = None
+    sample = logits[:m]
     if wl.dtype != "f32":
-        # bf16 rounding creates exact top-2 ties; the reference's topk order among equal probabilities is arbitrary, so
-        # regions holding such a pixel have no defined reference value and are left out (their number is reported)
-        top = host[0].topk(2, dim=1).values
-        tied = (top[:, 0] == top[:, 1]).reshape(m, -1)
-        dirty = torch.zeros((m, wl.nseg), dtype=torch.bool)
-        for i in range(m):
-            ids = host[1][i].reshape(-1)[tied[i]]
-            dirty[i, ids] = True
-        tie_free = (~dirty).numpy()
-    out = compare_with_cpu(wl, scores.cpu().numpy(), keys, cpu, tie_free)
+        sample = torch.cat([tie_free_device(sample[i:i + 4], wl.temp) for i in range(0, m, 4)])
+    scores, keys = gpu_mini_round(ctx, wl, sample, spx[:m], cost_dev, budget, None, rank_t)
+    host = (sample.float().cpu(), spx[:m].long().cpu())
+    cpu = cpu_round(wl, m, host, cost_all, budget)
+    out = compare_with_cpu(wl, scores.cpu().numpy(), keys, cpu)
     out.update({"images": m, "budget": budget, "against": "oracle port of the reference's torch ops on the same images (host copies of the resident inputs)"})
-    if tie_free is not None:
-        out["regions_with_tied_pixels_excluded"] = int((~tie_free).sum())
+    if wl.dtype != "f32":
+        out["note"] = ("bf16 inputs: pixels whose two largest logits round to the same bf16 value were nudged apart first (the reference's "
+                       "topk order among equal probabilities is arbitrary); both sides read the same bf16-representable values")
     return out, host, cpu
 
 
@@ -726,7 +736,8 @@ def run_losses(ctx: Ctx, rho: float, steps: int):
     got_total.backward()
     torch.cuda.synchronize()
     ref_grad, got_grad = xr.grad.numpy(), xg.grad.cpu().numpy()
-    val_err = max(abs(float(g) - float(r)) / max(abs(float(r)), 1e-30) for g, r in zip(got_parts, ref_parts))
+    as_float = lambda v: float(v.detach()) if torch.is_tensor(v) else float(v)      # noqa: E731  (an empty bucket is a python 0)
+    val_err = max(abs(as_float(g) - as_float(r)) / max(abs(as_float(r)), 1e-30) for g, r in zip(got_parts, ref_parts))
     grad_err = float(np.max(np.abs(got_grad - ref_grad)) / max(float(np.abs(ref_grad).max()), 1e-30))
     out["cpu_baseline"] = {"value": m / sec, "unit": "crops/s", "cores": torch.get_num_threads(), "kind": "port",
                            "sample": f"{m} of the 16 crops, oracle port fwd+bwd (autograd) in {sec:.1f} s"}

@@ -47,6 +47,16 @@ def test_every_selector_family_matches_the_oracle_at_baseline_shapes(shape):
     spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=22, drop_ids=2)
     pool = batches(logits, spx, bs)          # reference batching: the mean-of-batch-means has a short last batch for VOC
     hist_ref = oa.region_histograms(pool, nseg, temp).numpy()
+    # Normalised selectors compute (u - min) / (max - min): a relative error e on the region means u (1e-5 allowed; the
+    # oracle's own sequential fp32 sums of ~1000 pixels carry ~2e-6) becomes e * u / (max - min) ABSOLUTE on the [0, 1]
+    # scale.  The region means of i.i.d. synthetic logits sit in a narrow band, so that factor is ~5-10 here; the
+    # tolerance of the normalised comparisons is scaled by it (still 1e-5 relative on what the kernels compute).
+    raw = torch.cat([oa._segment_mean(oa.softmax_bvsb(p, temp)[0], s, nseg) for p, s in pool]).view(-1)
+    raw = raw[raw != 0]
+    amp = float(raw.max() / (raw.max() - raw.min()))
+
+    def close_normalised(got, ref):
+        np.testing.assert_allclose(got.astype(np.float64), ref.astype(np.float64), rtol=1e-5, atol=1e-5 * max(amp, 1.0), err_msg=name)
 
     got, stats = _engine("my_bvsb_predclsbal_pwr_banignore", logits, spx, nseg, temp, coeff, bs)
     np.testing.assert_array_equal(stats.cls_cnt.cpu().numpy().astype(np.int64), hist_ref)           # integer: bit-exact
@@ -56,14 +66,17 @@ def test_every_selector_family_matches_the_oracle_at_baseline_shapes(shape):
     assert_scores_close(got, oa.scores_predclsbal_pwr(pool, nseg, temp, coeff, ban_ignore=False).numpy(), False, name)
 
     got, _ = _engine("my_bvsb_banignore", logits, spx, nseg, temp, coeff, bs)
-    assert_scores_close(got, oa.scores_my_bvsb_banignore(pool, nseg, temp).numpy(), True, name)
+    close_normalised(got, oa.scores_my_bvsb_banignore(pool, nseg, temp).numpy())
 
     got, _ = _engine("my_bvsb_clsbal_v2_banignore", logits, spx, nseg, temp, coeff, bs)
-    assert_scores_close(got, oa.scores_clsbal_v2(pool, nseg, temp, ban_ignore=True).numpy(), True, name)
+    close_normalised(got, oa.scores_clsbal_v2(pool, nseg, temp, ban_ignore=True).numpy())
 
     # plain my_bvsb on a predignore net: the ignore channel is sliced off and read in place through the image stride
     got, _ = _engine("my_bvsb", logits, spx, nseg, temp, coeff, bs, predignore=True)
-    assert_scores_close(got, oa.scores_my_bvsb(pool, nseg, temp, predignore=True).numpy(), True, name)
+    raw = torch.cat([oa._segment_mean(oa.softmax_bvsb(p[:, :-1], temp)[0], s, nseg) for p, s in pool]).view(-1)
+    raw = raw[raw != 0]
+    amp = float(raw.max() / (raw.max() - raw.min()))
+    close_normalised(got, oa.scores_my_bvsb(pool, nseg, temp, predignore=True).numpy())
 
 
 def test_bf16_logits_weighted_selector_matches_the_oracle_on_tie_free_pixels():
