@@ -92,6 +92,18 @@ int mas_bvsb_segment_stats_multi_dev(int n_segments, const void* const* logits, 
                                      int width, int nseg, float temperature, float* cls_sum, int32_t* cls_cnt,
                                      double* prob_sum, void* stream);
 
+/* mas_bvsb_segment_stats_lowres_dev -- the same pass fed with the network head's LOW-RESOLUTION logits
+ * (n_img, channels, height_in, width_in): every full-resolution logit is produced on the fly exactly as the model's final
+ * F.interpolate(x, size=(height, width), mode='bilinear', align_corners=False) would (models/segmentation/utils.py:28-34,
+ * deeplabv3.py:115-129; source index = (in/out) * (dst + 0.5) - 0.5 clamped at 0, taps i0 and min(i0 + 1, in - 1)), so
+ * the 16x larger up-sampled tensor is never written nor read.  Opt-in: it changes what the
+ * caller hands over (the head's output instead of net(images)); results equal mas_bvsb_segment_stats_dev on the
+ * interpolated tensor up to fp32 rounding of the interpolation.  ids stay full resolution (height, width).
+ */
+int mas_bvsb_segment_stats_lowres_dev(const void* logits, int logits_dtype, int64_t image_stride, int height_in, int width_in,
+                                      const int32_t* ids, int n_img, int channels, int height, int width, int nseg,
+                                      float temperature, float* cls_sum, int32_t* cls_cnt, double* prob_sum, void* stream);
+
 /* mas_class_weights_dev -- w_c = (coeff * pbar_c + 1)^-2, pbar = the reference's `cumulated_pred_prob / len(loader)`
  * (active_selection/my_bvsb_predclsbal_pwr.py:33-47): per reference batch of `ref_batch` images (the last may be short)
  * the mean probability of class c = sum of prob_sum rows / (images * pixels_per_image), accumulated over the batches in

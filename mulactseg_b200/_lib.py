@@ -31,6 +31,8 @@ SIGNATURES = {
     "mas_kernel_launches": (c_int64, []),
     "mas_bvsb_segment_stats_dev": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                                            c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mas_bvsb_segment_stats_lowres_dev": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                                  c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mas_class_weights_dev": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int, c_float, c_void_p, c_void_p]),
     "mas_prefix_cut_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "mas_bvsb_segment_stats_multi_dev": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

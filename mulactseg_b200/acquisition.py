@@ -170,6 +170,42 @@ class RegionStats:
             self.flush()
 
 
+def _add_batch_lowres(self, first_img: int, logits_lo: torch.Tensor, spx: torch.Tensor, temperature: float) -> None:
+    """Fold images [first_img, first_img + B) into the tables from the network head's LOW-RESOLUTION logits
+    (B,C',h,w): the final ``F.interpolate(..., size=spx.shape[1:], mode='bilinear', align_corners=False)`` of the model
+    (models/segmentation/utils.py:28-34) is evaluated inside the kernel, so the 16x larger tensor never exists
+    (opt-in -- the caller hands over the head's output instead of ``net(images)``)."""
+    b = logits_lo.shape[0]
+    if first_img < 0 or first_img + b > self.n_img:
+        raise RuntimeError(f"batch [{first_img},{first_img + b}) outside the shard of {self.n_img} images")
+    if logits_lo.shape[1] != self.channels:
+        raise RuntimeError(f"expected {self.channels} channels, got {logits_lo.shape[1]}")
+    if spx.dtype != torch.int32:
+        spx = spx.to(torch.int32)
+    spx = spx.contiguous()
+    pixels = spx.shape[1] * spx.shape[2]
+    if self._prob_sum is not None and self.pixels_per_image not in (None, pixels):
+        raise RuntimeError("add_batch_lowres: the predclsbal selectors need one image size per pool")
+    self.pixels_per_image = pixels
+    self.flush()                       # keeps the table rows in launch order with queued full-resolution batches
+    tables = (self._cls_sum[first_img:first_img + b], self._cls_cnt[first_img:first_img + b],
+              None if self._prob_sum is None else self._prob_sum[first_img:first_img + b])
+    self.launches += 1
+    if not self.lanes:
+        ops.bvsb_segment_stats_lowres(logits_lo, spx, self.nseg, temperature, *tables)
+        return
+    lane = self.lanes[self._turn % len(self.lanes)]
+    self._turn += 1
+    lane.wait_stream(torch.cuda.current_stream(self._cls_sum.device))
+    ops.bvsb_segment_stats_lowres(logits_lo, spx, self.nseg, temperature, *tables, stream=lane.cuda_stream)
+    logits_lo.record_stream(lane)
+    spx.record_stream(lane)
+    self._dirty = True
+
+
+RegionStats.add_batch_lowres = _add_batch_lowres
+
+
 def finalize(stats: RegionStats, spec: SelectorSpec, coeff: float = 0.0, ref_batch: int = 1, group=None, shard_counts=None):
     """Selector epilogue -> (scores (n,S) f32, dominant (n,S) i32) on the device.
 

@@ -25,8 +25,7 @@
 //     one for the ids per strip row, completion is signalled on a per-stage mbarrier.  Bytes in flight
 //     do not depend on registers or on the warp being scheduled.
 //   * LDG (any shape): 128-bit (VEC = 4) or scalar (VEC = 1) streaming loads straight to registers.
-#include "common.cuh"
-#include "walk.cuh"
+#include "scorer.cuh"
 
 #include <cuda.h>  // CUtensorMap and enums only; the encoder is resolved through cudaGetDriverEntryPoint
 #include <stdlib.h>
@@ -34,216 +33,9 @@
 #include <algorithm>
 #include <mutex>
 
+using namespace mas_scorer;
+
 namespace {
-
-constexpr int kLdgThreads = 128;
-constexpr int kTmaMaxWarps = 8;
-constexpr int kTmaStripPx = 128;  // pixels per strip row on the TMA path (32 lanes x 4)
-
-// A launch covers up to kMaxSeg SEGMENTS: batches of images that live in different allocations (consecutive loader
-// batches) but fill consecutive rows of the tables.  Images are numbered 0 .. n_img-1 across the segments.
-constexpr int kMaxSeg = MAS_MAX_SEGMENTS;
-
-struct StatsParams {
-    const void* seg_logits[kMaxSeg];
-    const int32_t* seg_ids[kMaxSeg];
-    long long seg_stride[kMaxSeg];   // elements between images of the segment's logits
-    int seg_first[kMaxSeg + 1];      // first image of segment g; seg_first[n_seg] = n_img
-    int n_seg;
-    int n_img, C, H, W, S;
-    float scale;             // log2(e) / T
-    int strips;              // column strips per image
-    long long total_rows;    // n_img * strips * H strip rows
-    int stages;              // TMA path: ring depth per warp
-    float* cls_sum;
-    int32_t* cls_cnt;
-    double* prob_sum;
-};
-
-__device__ __forceinline__ int seg_of(const StatsParams& p, int img) {
-    int g = 0;
-    while (g + 1 < p.n_seg && img >= p.seg_first[g + 1]) ++g;
-    return g;
-}
-
-// ------------------------------------------------------------------------------------------ loads
-template <typename T, int VEC>
-struct VecLoad;
-
-template <>
-struct VecLoad<float, 4> {
-    // volatile: keeps the C' plane loads of a row back to back (memory-level parallelism) instead of
-    // letting the compiler sink each one next to its first use
-    static __device__ __forceinline__ void global(const float* p, float (&o)[4]) {
-        asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "l"(p));
-    }
-    static __device__ __forceinline__ void shared(const float* p, float (&o)[4]) {
-        const float4 v = *reinterpret_cast<const float4*>(p);
-        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-    }
-};
-template <>
-struct VecLoad<float, 1> {
-    static __device__ __forceinline__ void global(const float* p, float (&o)[1]) { o[0] = __ldcs(p); }
-};
-template <>
-struct VecLoad<__nv_bfloat16, 4> {
-    static __device__ __forceinline__ void unpack(const uint2 v, float (&o)[4]) {
-        o[0] = __uint_as_float(v.x << 16); o[1] = __uint_as_float(v.x & 0xffff0000u);
-        o[2] = __uint_as_float(v.y << 16); o[3] = __uint_as_float(v.y & 0xffff0000u);
-    }
-    static __device__ __forceinline__ void global(const __nv_bfloat16* p, float (&o)[4]) {
-        uint2 q;
-        asm volatile("ld.global.cs.v2.u32 {%0, %1}, [%2];" : "=r"(q.x), "=r"(q.y) : "l"(p));
-        unpack(q, o);
-    }
-    static __device__ __forceinline__ void shared(const __nv_bfloat16* p, float (&o)[4]) {
-        unpack(*reinterpret_cast<const uint2*>(p), o);
-    }
-};
-template <>
-struct VecLoad<__nv_bfloat16, 1> {
-    static __device__ __forceinline__ void global(const __nv_bfloat16* p, float (&o)[1]) {
-        const unsigned short v = __ldcs(reinterpret_cast<const unsigned short*>(p));
-        o[0] = __uint_as_float(((uint32_t)v) << 16);
-    }
-};
-
-template <int VEC>
-__device__ __forceinline__ void load_ids(const int32_t* p, int (&o)[VEC]);
-template <>
-__device__ __forceinline__ void load_ids<4>(const int32_t* p, int (&o)[4]) {
-    const int4 v = __ldcs(reinterpret_cast<const int4*>(p));
-    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-}
-template <>
-__device__ __forceinline__ void load_ids<1>(const int32_t* p, int (&o)[1]) { o[0] = __ldcs(p); }
-
-// ------------------------------------------------------------------------------------------ per-thread walker
-// State a thread carries down its strip: the superpixel whose partial sums live in its private
-// shared-memory column, and (when needed) the running softmax sums of the current image.
-template <int CMAX, bool EXACT, int VEC, bool NEED_PROB>
-struct Walker {
-    uint2* col;       // slot of class c: col[c * col_stride]  {float sum bits, int count}
-    int col_stride;   // threads per CTA
-    int C, S;
-    float scale;
-    float* cls_sum;
-    int32_t* cls_cnt;
-    long long img_region;  // index of region 0 of the current image
-    int cur;
-    float pacc[NEED_PROB ? CMAX : 1];
-
-    __device__ __forceinline__ void init(uint2* column, int stride, const StatsParams& p) {
-        col = column; col_stride = stride;
-        C = EXACT ? CMAX : p.C; S = p.S; scale = p.scale;
-        cls_sum = p.cls_sum; cls_cnt = p.cls_cnt;
-        img_region = 0; cur = -1;
-        for (int c = 0; c < C; ++c) col[c * col_stride] = make_uint2(0u, 0u);
-        if (NEED_PROB) {
-#pragma unroll
-            for (int c = 0; c < CMAX; ++c) pacc[c] = 0.f;
-        }
-    }
-
-    // flush the private {sum,count} column into the global tables of the current superpixel
-    __device__ __forceinline__ void flush() {
-        if (cur < 0) return;
-        const long long base = (img_region + cur) * C;
-        for (int c = 0; c < C; ++c) {
-            const uint2 slot = col[c * col_stride];
-            if (slot.y != 0u) {
-                atomicAdd(cls_sum + base + c, __uint_as_float(slot.x));
-                atomicAdd(cls_cnt + base + c, (int)slot.y);
-                col[c * col_stride] = make_uint2(0u, 0u);
-            }
-        }
-        cur = -1;
-    }
-
-    // whole warp: add the running softmax sums of image `img` to prob_sum and restart them
-    __device__ __forceinline__ void flush_prob(double* prob_sum, int img, int lane) {
-        if (!NEED_PROB) return;
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c) {
-            float x = pacc[c];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-            if (lane == 0 && (EXACT || c < C) && x != 0.f) atomicAdd(prob_sum + (size_t)img * C + c, (double)x);
-            pacc[c] = 0.f;
-        }
-    }
-
-    __device__ __forceinline__ void row(float (&v)[CMAX][VEC], const int (&id)[VEC]) {
-        // ---- pure arithmetic first, the VEC pixels in lock step (independent chains interleave)
-        float m1[VEC], m2[VEC], bvsb[VEC];
-        int top1[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) { m1[j] = v[0][j]; m2[j] = -INFINITY; top1[j] = 0; }
-#pragma unroll
-        for (int c = 1; c < CMAX; ++c) {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const float x = v[c][j];
-                const bool gt = x > m1[j];          // strict: the first index keeps a tie
-                m2[j] = fmaxf(m2[j], gt ? m1[j] : x);
-                top1[j] = gt ? c : top1[j];
-                m1[j] = gt ? x : m1[j];
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) bvsb[j] = mas::ex2_approx((m2[j] - m1[j]) * scale) + 1e-8f;
-        if (NEED_PROB) {
-            float shift[VEC], den_a[VEC], den_b[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) { shift[j] = -m1[j] * scale; den_a[j] = 0.f; den_b[j] = 0.f; }
-#pragma unroll
-            for (int c = 0; c < CMAX; ++c) {
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    v[c][j] = mas::ex2_approx(fmaf(v[c][j], scale, shift[j]));   // padded planes hold -inf -> 0
-                    if (c & 1) den_b[j] += v[c][j]; else den_a[j] += v[c][j];
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) den_a[j] = mas::rcp_approx(den_a[j] + den_b[j]);
-#pragma unroll
-            for (int c = 0; c < CMAX; ++c) {
-                float t = pacc[c];
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) t = fmaf(v[c][j], den_a[j], t);
-                pacc[c] = t;
-            }
-        }
-        // ---- then the segmented accumulation
-        // does this row still touch the current superpixel?  if not, move on to the row's first id
-        // ids outside [0, S) (crop padding, -1, garbage) become -2: never equal to `cur` (>= -1), never accumulated
-        int sid[VEC];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) sid[j] = ((unsigned)id[j] < (unsigned)S) ? id[j] : -2;
-        bool touches = false;
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) touches |= (sid[j] == cur);
-        if (!touches) {
-            flush();
-            cur = sid[0] >= 0 ? sid[0] : -1;
-        }
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const int s = sid[j];
-            if (s == cur) {
-                uint2 slot = col[top1[j] * col_stride];
-                slot.x = __float_as_uint(__uint_as_float(slot.x) + bvsb[j]);
-                slot.y += 1u;
-                col[top1[j] * col_stride] = slot;
-            } else if (s >= 0) {
-                const long long r = (img_region + s) * C + top1[j];
-                atomicAdd(cls_sum + r, bvsb[j]);
-                atomicAdd(cls_cnt + r, 1);
-            }
-        }
-    }
-};
 
 // ------------------------------------------------------------------------------------------ LDG path
 template <int CMAX, bool EXACT, int VEC, bool NEED_PROB, typename T>
@@ -595,7 +387,7 @@ cudaError_t launch_tma(StatsParams p, cudaStream_t stream, bool* unsupported) {
     return cudaGetLastError();
 }
 
-enum Path { kPathLdg1 = 0, kPathLdg4 = 1, kPathTma = 2 };
+enum Path { kPathLdg1 = 0, kPathLdg4 = 1, kPathTma = 2, kPathAbreast1 = 3, kPathAbreast4 = 4 };
 
 template <int CMAX, bool EXACT, bool NEED_PROB, typename T>
 cudaError_t launch_path(const StatsParams& p, int path, cudaStream_t stream) {
@@ -667,18 +459,23 @@ extern "C" int mas_bvsb_segment_stats_multi_dev(int n_segments, const void* cons
     }
     MAS_REQUIRE((long long)p.n_img * ((width + 31) / 32) * height < (1ll << 40), MAS_E_RANGE, "bvsb_segment_stats: too many rows");
     tma_ok = tma_ok && vec4;
-    int path = tma_ok ? kPathTma : (vec4 ? kPathLdg4 : kPathLdg1);
-    const char* forced = getenv("MAS_SCORER_PATH");   // development switch: "ldg" keeps the register path
-    if (forced && forced[0] == 'l' && path == kPathTma) path = kPathLdg4;
+    // default: TMA ring when every row is 16-byte aligned, else the abreast kernel (adjacent strips per CTA + L1 prefetch)
+    int path = tma_ok ? kPathTma : (vec4 ? kPathAbreast4 : kPathAbreast1);
+    const char* forced = getenv("MAS_SCORER_PATH");   // development / test switch: "ldg" = plain register path, "abreast"
+    if (forced && forced[0] == 'l') path = vec4 ? kPathLdg4 : kPathLdg1;
+    if (forced && forced[0] == 'a') path = vec4 ? kPathAbreast4 : kPathAbreast1;
 
     p.C = channels; p.H = height; p.W = width; p.S = nseg;
     p.scale = 1.4426950408889634f / temperature;
     p.strips = 0; p.total_rows = 0; p.stages = 0;
     p.cls_sum = cls_sum; p.cls_cnt = cls_cnt; p.prob_sum = prob_sum;
+    p.h_in = 0; p.w_in = 0; p.ry = 1.f; p.rx = 1.f;
 
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
-    if (logits_dtype == MAS_F32)
+    if (path == kPathAbreast1 || path == kPathAbreast4)
+        e = launch_abreast(p, path == kPathAbreast4 ? 4 : 1, false, logits_dtype, st);
+    else if (logits_dtype == MAS_F32)
         e = prob_sum ? dispatch_channels<true, float>(p, path, st) : dispatch_channels<false, float>(p, path, st);
     else
         e = prob_sum ? dispatch_channels<true, __nv_bfloat16>(p, path, st) : dispatch_channels<false, __nv_bfloat16>(p, path, st);
@@ -694,4 +491,37 @@ extern "C" int mas_bvsb_segment_stats_dev(const void* logits, int logits_dtype, 
     MAS_REQUIRE(n_img >= 0, MAS_E_BADARG, "bvsb_segment_stats: bad shape");
     return mas_bvsb_segment_stats_multi_dev(1, &logits, logits_dtype, &image_stride, &ids, &n_img, channels, height, width, nseg,
                                             temperature, cls_sum, cls_cnt, prob_sum, stream);
+}
+
+extern "C" int mas_bvsb_segment_stats_lowres_dev(const void* logits, int logits_dtype, int64_t image_stride, int height_in, int width_in,
+                                                 const int32_t* ids, int n_img, int channels, int height, int width, int nseg,
+                                                 float temperature, float* cls_sum, int32_t* cls_cnt, double* prob_sum, void* stream) {
+    MAS_REQUIRE(logits && ids && cls_sum && cls_cnt, MAS_E_BADARG, "bvsb_segment_stats_lowres: null pointer");
+    MAS_REQUIRE(n_img >= 0 && height > 0 && width > 0 && nseg > 0 && height_in > 0 && width_in > 0, MAS_E_BADARG,
+                "bvsb_segment_stats_lowres: bad shape");
+    MAS_REQUIRE(height_in <= height && width_in <= width, MAS_E_BADARG, "bvsb_segment_stats_lowres: the source must not be larger than the id map");
+    MAS_REQUIRE(channels >= 2 && channels <= MAS_MAX_CLASSES, MAS_E_RANGE, "bvsb_segment_stats_lowres: channels=%d outside [2,%d]", channels,
+                MAS_MAX_CLASSES);
+    MAS_REQUIRE(temperature > 0.f, MAS_E_BADARG, "bvsb_segment_stats_lowres: temperature must be > 0");
+    MAS_REQUIRE(logits_dtype == MAS_F32 || logits_dtype == MAS_BF16, MAS_E_BADARG, "bvsb_segment_stats_lowres: bad dtype");
+    if (n_img == 0) return 0;
+    const long long plane_in = (long long)height_in * width_in;
+    if (image_stride == 0) image_stride = (long long)channels * plane_in;
+    MAS_REQUIRE(image_stride >= (long long)channels * plane_in, MAS_E_BADARG, "bvsb_segment_stats_lowres: image_stride too small");
+    MAS_REQUIRE((long long)n_img * ((width + 31) / 32) * height < (1ll << 40), MAS_E_RANGE, "bvsb_segment_stats_lowres: too many rows");
+    StatsParams p;
+    p.n_seg = 1; p.n_img = n_img;
+    for (int g = 0; g < kMaxSeg; ++g) { p.seg_logits[g] = logits; p.seg_ids[g] = ids; p.seg_stride[g] = image_stride; p.seg_first[g + 1] = n_img; }
+    p.seg_first[0] = 0;
+    p.C = channels; p.H = height; p.W = width; p.S = nseg;
+    p.scale = 1.4426950408889634f / temperature;
+    p.strips = 0; p.total_rows = 0; p.stages = 0;
+    p.cls_sum = cls_sum; p.cls_cnt = cls_cnt; p.prob_sum = prob_sum;
+    p.h_in = height_in; p.w_in = width_in;
+    // torch's area_pixel_compute_scale<float>(input, output, align_corners=false, no scale factor): (float)input / output
+    p.ry = (float)height_in / (float)height; p.rx = (float)width_in / (float)width;
+    const bool vec4 = (width % 4 == 0) && (((uintptr_t)ids) % 16 == 0);       // only the id map is read with 128-bit loads
+    cudaError_t e = launch_abreast(p, vec4 ? 4 : 1, true, logits_dtype, (cudaStream_t)stream);
+    if (e != cudaSuccess) return mas::cuda_fail(e, "bvsb_stats lowres kernel launch");
+    return 0;
 }

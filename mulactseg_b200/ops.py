@@ -135,6 +135,42 @@ def bvsb_segment_stats_multi(batches, nseg: int, temperature: float, cls_sum: to
                   cls_sum.data_ptr(), cls_cnt.data_ptr(), _ptr(prob_sum), _stream(first) if stream is None else int(stream))
 
 
+def bvsb_segment_stats_lowres(logits_lo: torch.Tensor, spx: torch.Tensor, nseg: int, temperature: float,
+                              cls_sum: torch.Tensor, cls_cnt: torch.Tensor, prob_sum: Optional[torch.Tensor],
+                              stream: Optional[int] = None) -> None:
+    """``bvsb_segment_stats`` fed with the head's low-resolution logits (B,C,h,w): the bilinear up-sampling to the id
+    map's (H,W) (``F.interpolate(..., align_corners=False)``) happens inside the kernel
+    (``mas_bvsb_segment_stats_lowres_dev``)."""
+    if not isinstance(logits_lo, torch.Tensor) or not logits_lo.is_cuda:
+        raise RuntimeError("logits: expected a CUDA tensor (there is no CPU path)")
+    if logits_lo.dim() != 4 or logits_lo.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"logits: expected (B,C,h,w) float32/bfloat16, got {tuple(logits_lo.shape)} {logits_lo.dtype}")
+    _want(spx, "spx", torch.int32, 3)
+    b, c, h_in, w_in = logits_lo.shape
+    if b * c * h_in * w_in > 0 and (logits_lo.stride(3) != 1 or logits_lo.stride(2) != w_in or logits_lo.stride(1) != h_in * w_in
+                                    or (b > 1 and logits_lo.stride(0) < c * h_in * w_in)):
+        raise RuntimeError("logits: expected NCHW layout with contiguous planes")
+    image_stride = logits_lo.stride(0) if b > 1 else c * h_in * w_in
+    if spx.shape[0] != b or spx.shape[1] < h_in or spx.shape[2] < w_in:
+        raise RuntimeError(f"spx shape {tuple(spx.shape)} does not match low-resolution logits {tuple(logits_lo.shape)}")
+    h, w = spx.shape[1:]
+    _want(cls_sum, "cls_sum", torch.float32)
+    _want(cls_cnt, "cls_cnt", torch.int32)
+    if cls_sum.numel() != b * nseg * c or cls_cnt.numel() != b * nseg * c:
+        raise RuntimeError("cls_sum / cls_cnt must hold B*nseg*C elements")
+    if prob_sum is not None:
+        _want(prob_sum, "prob_sum", torch.float64)
+        if prob_sum.numel() != b * c:
+            raise RuntimeError("prob_sum must hold B*C elements")
+    if b == 0:
+        return
+    with _on(logits_lo):
+        _lib.call("mas_bvsb_segment_stats_lowres_dev", logits_lo.data_ptr(),
+                  _lib.MAS_F32 if logits_lo.dtype == torch.float32 else _lib.MAS_BF16, int(image_stride), h_in, w_in, spx.data_ptr(),
+                  b, c, h, w, int(nseg), float(temperature), cls_sum.data_ptr(), cls_cnt.data_ptr(), _ptr(prob_sum),
+                  _stream(logits_lo) if stream is None else int(stream))
+
+
 def class_weights(prob_sum: torch.Tensor, pixels_per_image: int, ref_batch: int, coeff: float) -> torch.Tensor:
     """(N,C) f64 per-image probability sums in pool order -> (C,) f32 class weights (``mas_class_weights_dev``)."""
     _want(prob_sum, "prob_sum", torch.float64, 2)

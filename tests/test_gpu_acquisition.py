@@ -57,9 +57,10 @@ def test_selectors_match_reference_golden(case):
                                    (5, 20, 24, 200, 64, "jitter"), (3, 22, 37, 132, 150, "jitter"),
                                    (9, 19, 8, 260, 16, "grid")])
 @pytest.mark.parametrize("method", ["my_bvsb_predclsbal_pwr_banignore", "my_bvsb_clsbal_v2"])
-@pytest.mark.parametrize("path", ["tma", "ldg"])
+@pytest.mark.parametrize("path", ["tma", "ldg", "abreast"])
 def test_selectors_match_oracle(shape, method, path, monkeypatch):
-    """Both data paths of the scorer (TMA ring where rows are 16-byte aligned, LDG otherwise / when forced)."""
+    """Every data path of the scorer: TMA ring where rows are 16-byte aligned, the abreast kernel otherwise (or when
+    forced), the plain register path when forced ("tma" = the default choice for the shape)."""
     monkeypatch.setenv("MAS_SCORER_PATH", path)
     n, c, h, w, nseg, kind = shape
     logits = synth.logits(n, c, h, w, "cosine", seed=n * c + h)
@@ -158,7 +159,7 @@ def test_voc_size_properties(shape):
     assert float(score[dominant == c - 1].abs().max() if (dominant == c - 1).any() else 0.0) == 0.0
 
 
-@pytest.mark.parametrize("path", ["tma", "ldg"])
+@pytest.mark.parametrize("path", ["tma", "ldg", "abreast"])
 @pytest.mark.parametrize("shape", [(11, 19, 24, 128, 40, 1), (21, 22, 37, 132, 150, 2), (8, 6, 9, 33, 7, 3)])
 def test_grouped_launches_equal_single_launches(shape, path, monkeypatch):
     """Several loader batches (separate allocations, short last batch, more batches than one launch takes) folded by
@@ -227,7 +228,7 @@ def test_ids_outside_range_are_ignored_and_empty_batch():
     stats.add_batch(0, logits[:0], spx[:0], 1.0)  # empty batch is a no-op
 
 
-@pytest.mark.parametrize("path", ["tma", "ldg"])
+@pytest.mark.parametrize("path", ["tma", "ldg", "abreast"])
 @pytest.mark.parametrize("bad", [-1, -7, 2 ** 31 - 1, "nseg"])
 def test_invalid_ids_before_valid_ones_do_not_leak(path, bad, monkeypatch):
     """A thread that meets out-of-range ids BEFORE its first valid superpixel (top rows of -1 / pad / garbage) must not
@@ -446,3 +447,41 @@ def test_host_entry_matches_device_path():
     tie = (keys & np.uint64(0xFFFFFFFF)).astype(np.int64)
     assert list(zip((tie // nseg).tolist(), (tie % nseg).tolist())) == [(r, s) for _, r, s in cand[:k]]
     assert rank_sorted.tolist() == list(range(n))
+
+
+@pytest.mark.parametrize("shape", [(3, 20, 16, 32, 64, 128, 96, torch.float32), (2, 22, 33, 33, 129, 129, 40, torch.float32),
+                                   (2, 19, 10, 13, 37, 50, 12, torch.float32), (3, 21, 24, 32, 94, 125, 30, torch.bfloat16),
+                                   (1, 6, 8, 8, 8, 8, 4, torch.float32), (2, 20, 64, 128, 256, 512, 512, torch.float32)])
+def test_lowres_entry_matches_oracle_on_the_interpolated_logits(shape):
+    """the scorer fed with the head's low-resolution logits must equal the reference path applied to
+    F.interpolate(logits, size, mode='bilinear', align_corners=False) (models/segmentation/utils.py:28-34) -- integer x4
+    (Cityscapes: 256x512 -> 1024x2048), the VOC ratio 129 -> 513, odd sizes, bf16 source, identity size."""
+    from mulactseg_b200 import acquisition as acq
+    n, c, h_in, w_in, h, w, nseg, dtype = shape
+    low = synth.logits(n, c, h_in, w_in, "cosine", seed=h + w).to(dtype)
+    spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=9, drop_ids=1 if nseg > 8 else 0)
+    full = torch.nn.functional.interpolate(low.float(), size=(h, w), mode="bilinear", align_corners=False)
+    pool = batches(full, spx, 2)
+    ref = oa.scores_predclsbal_pwr(pool, nseg, 0.1, 6.0, ban_ignore=True)
+    spec = acq.SELECTORS["my_bvsb_predclsbal_pwr_banignore"]
+    stats = acq.RegionStats(n, nseg, c, DEV, need_prob=True)
+    x, ids = low.to(DEV), spx.to(DEV, torch.int32)
+    for i in range(0, n, 2):
+        stats.add_batch_lowres(i, x[i:i + 2], ids[i:i + 2], 0.1)
+    score, _ = acq.finalize(stats, spec, 6.0, 2)
+    # interpolated logits of neighbouring classes can come within an ulp of each other, where our interpolation (same
+    # expression as torch's CUDA kernel) and torch's CPU kernel may round differently and flip an arg-max: compare the
+    # histograms on pixels whose top-2 gap exceeds the rounding, the scores at the north_star tolerance
+    top2 = full.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-5
+    cnt = stats.cls_cnt.cpu().long()
+    assert cnt.sum(dim=(1, 2)).tolist() == [int((spx[i] < nseg).sum()) for i in range(n)]
+    if bool(safe.all()):
+        np.testing.assert_array_equal(cnt.numpy(), oa.region_histograms(pool, nseg, 0.1).numpy())
+    assert_scores_close(score.cpu().numpy(), ref.numpy(), False, str(shape))
+    # and equal to our own full-resolution kernels on the interpolated tensor (same tolerance, independent path)
+    stats_full = acq.RegionStats(n, nseg, c, DEV, need_prob=True)
+    stats_full.add_batch(0, full.to(DEV), ids, 0.1)
+    score_full, _ = acq.finalize(stats_full, spec, 6.0, 2)
+    np.testing.assert_allclose(score.cpu().numpy(), score_full.cpu().numpy(), rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(stats.prob_sum.cpu().numpy(), stats_full.prob_sum.cpu().numpy(), rtol=1e-5)
