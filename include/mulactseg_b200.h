@@ -347,6 +347,24 @@ int mas_proto_labeller_dev(const float* feats, int feat_channels, const float* l
                            int height, int width, int nseg, int only_multihot, int threshold_mode,
                            uint8_t* labels, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
+/* mas_proto_labeller_src_dev -- mas_proto_labeller_dev with a described FEATURE SOURCE (north_star: "stream bf16/fp32 ...
+ * features"):
+ *   feat_dtype MAS_F32 | MAS_BF16 (bf16 features are widened to fp32; every similarity is still an fp32 FMA chain);
+ *   (feat_height, feat_width) == (height, width): full-resolution features as in the reference
+ *   (trainer/eval_save_cosplbl_prop.py:55-60, feats = the x4 up-sampled head features);
+ *   smaller: the network head's LOW-RESOLUTION (F, feat_height, feat_width) map -- every feature value is evaluated on
+ *   the fly as F.interpolate(feat, size=(height, width), mode='bilinear', align_corners=False) would produce it
+ *   (models/segmentation/utils.py:28-34, deeplabv3.py:122), so the 2.1 GB up-sampled tensor of a Cityscapes image is
+ *   never written nor read.  Labels equal mas_proto_labeller_dev on the interpolated tensor wherever similarities are
+ *   not within fp32 rounding of each other / of a threshold.  Everything else as mas_proto_labeller_dev (logits stay
+ *   full resolution: 8 % of the bytes).
+ */
+int mas_proto_labeller_src_dev(const void* feats, int feat_dtype, int feat_channels, int feat_height, int feat_width,
+                               const float* logits, int channels, const uint8_t* targets, int target_channels,
+                               const uint8_t* mask, const void* ids, int ids_dtype, int height, int width, int nseg,
+                               int only_multihot, int threshold_mode, uint8_t* labels, int32_t* status, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ offline multi-hot label generation
  *
  * mas_multihot_labels_dev -- ONE image of RegionCityscapesTensor.__getitem__ (dataloader/region_cityscapes_tensor.py:33-84,

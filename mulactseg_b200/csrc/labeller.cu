@@ -32,7 +32,9 @@ constexpr int kAssignThreads = 256;
 constexpr int kGroup = 8;          // prototypes evaluated per pass over a pixel's feature column
 
 struct LabelParams {
-    const float* feats;     // (F, H, W)
+    const void* feats;      // (F, H, W) -- or (F, fh_in, fw_in) when the features are low resolution (see FeatSource)
+    int fh_in, fw_in;       // low-resolution source size (0 = full resolution)
+    float fry, frx;         // fh_in / H, fw_in / W
     const uint8_t* mask;    // (H, W)
     const void* ids;        // (H, W)
     int F, C, H, W, S, P;
@@ -60,6 +62,63 @@ __device__ __forceinline__ int read_id(const void* ids, size_t i, int S) {
 __device__ __forceinline__ float ordered_to_float(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
+
+// ------------------------------------------------------------------------------------------ feature source
+// Where a pixel's F-dimensional feature column comes from.  Full resolution: element ch of pixel pix = feats[ch * P + pix]
+// (fp32, or bf16 widened to fp32).  LOW resolution (mas_proto_labeller_lowres_dev): feats holds the
+// network head's (F, fh_in, fw_in) map and every value is F.interpolate(mode='bilinear', align_corners=False)'s
+//   h0 * (w0 * a + w1 * b) + h1 * (w0 * d + w1 * e)          (models/segmentation/utils.py:28-34)
+// evaluated on the fly from the four taps -- the 16x larger (F, H, W) tensor (2.1 GB per Cityscapes image) never exists;
+// the low-resolution map (134 MB) mostly lives in L2.
+template <typename FT>
+__device__ __forceinline__ float feat_value(const FT* p);
+template <>
+__device__ __forceinline__ float feat_value<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float feat_value<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return __uint_as_float(((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
+}
+
+__device__ __forceinline__ void bilinear_tap(int dst, float scale, int size_in, int& i0, int& step, float& lambda1) {
+    float src = scale * ((float)dst + 0.5f) - 0.5f;      // torch: area_pixel_compute_source_index(align_corners=false)
+    src = src < 0.f ? 0.f : src;
+    i0 = (int)src;
+    if (i0 > size_in - 1) i0 = size_in - 1;
+    step = (i0 < size_in - 1) ? 1 : 0;
+    lambda1 = src - (float)i0;
+}
+
+template <typename FT, bool LOWRES>
+struct FeatColumn {
+    const FT* base;      // channel 0 of the pixel (LOWRES: of its top-left tap)
+    size_t plane;        // elements between channels
+    int right, down;     // LOWRES: offsets of the other taps
+    float l0x, l1x, l0y, l1y;
+
+    __device__ __forceinline__ FeatColumn(const LabelParams& p, int pix) {
+        if (LOWRES) {
+            const int y = pix / p.W, x = pix - y * p.W;
+            int y0, ys, x0, xs;
+            bilinear_tap(y, p.fry, p.fh_in, y0, ys, l1y);
+            bilinear_tap(x, p.frx, p.fw_in, x0, xs, l1x);
+            l0y = 1.f - l1y; l0x = 1.f - l1x;
+            plane = (size_t)p.fh_in * p.fw_in;
+            base = reinterpret_cast<const FT*>(p.feats) + (size_t)y0 * p.fw_in + x0;
+            right = xs; down = ys * p.fw_in;
+        } else {
+            plane = (size_t)p.P;
+            base = reinterpret_cast<const FT*>(p.feats) + pix;
+            right = 0; down = 0; l0x = l1x = l0y = l1y = 0.f;
+        }
+    }
+    __device__ __forceinline__ float at(int ch) const {
+        const FT* q = base + (size_t)ch * plane;
+        if (!LOWRES) return feat_value<FT>(q);
+        const float a = feat_value<FT>(q), b = feat_value<FT>(q + right);
+        const float d = feat_value<FT>(q + down), e = feat_value<FT>(q + down + right);
+        return l0y * (l0x * a + l1x * b) + l1y * (l0x * d + l1x * e);
+    }
+};
 
 // ------------------------------------------------------------------------------------------ P2
 template <typename IdT>
@@ -195,6 +254,7 @@ __global__ void spx_adjacency_kernel(const void* __restrict__ ids, int H, int W,
 
 // ------------------------------------------------------------------------------------------ prototypes
 // one warp per (superpixel, class): copy the feature column of the arg-max-probability pixel
+template <typename FT, bool LOWRES>
 __global__ void proto_gather_kernel(LabelParams p) {
     const long long entry = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -205,7 +265,8 @@ __global__ void proto_gather_kernel(LabelParams p) {
     const unsigned long long e = p.gmax[entry];
     if (e == 0ull) return;
     const uint32_t pix = ~(uint32_t)e;
-    for (int ch = lane; ch < p.F; ch += 32) p.proto[entry * p.F + ch] = p.feats[(size_t)ch * p.P + pix];
+    const FeatColumn<FT, LOWRES> col(p, (int)pix);
+    for (int ch = lane; ch < p.F; ch += 32) p.proto[entry * p.F + ch] = col.at(ch);
     if (lane == 0) atomicOr(p.svalid + (s >> 5), 1u << (s & 31));
 }
 
@@ -223,18 +284,19 @@ constexpr int kSlices = 4;         // CTAs that share the pixels of one superpix
 
 // sproto layout: [channel][kGroup] so that the kGroup operands of one channel are two 128-bit broadcast reads
 // (a 4-prototype instantiation for sparse batches was measured slower: the compiler keeps fewer loads in flight)
+template <typename FT, bool LOWRES>
 __device__ __forceinline__ void dot_all(const LabelParams& p, const float* __restrict__ sproto, int pix, float (&acc)[kGroup]) {
 #pragma unroll
     for (int g = 0; g < kGroup; ++g) acc[g] = 0.f;
-    const float* f = p.feats + pix;
-    const size_t P = (size_t)p.P;
+    const FeatColumn<FT, LOWRES> f(p, pix);
+    constexpr int kBatch = LOWRES ? kFeatBatch / 2 : kFeatBatch;     // LOWRES: four taps per value -- same number of loads in flight
     int ch = 0;
-    for (; ch + kFeatBatch <= p.F; ch += kFeatBatch) {
-        float x[kFeatBatch];
+    for (; ch + kBatch <= p.F; ch += kBatch) {
+        float x[kBatch];
 #pragma unroll
-        for (int i = 0; i < kFeatBatch; ++i) x[i] = __ldg(f + (size_t)(ch + i) * P);
+        for (int i = 0; i < kBatch; ++i) x[i] = f.at(ch + i);
 #pragma unroll
-        for (int i = 0; i < kFeatBatch; ++i) {
+        for (int i = 0; i < kBatch; ++i) {
             const float4 a = *reinterpret_cast<const float4*>(sproto + (size_t)(ch + i) * kGroup);
             const float4 b = *reinterpret_cast<const float4*>(sproto + (size_t)(ch + i) * kGroup + 4);
             acc[0] = fmaf(x[i], a.x, acc[0]); acc[1] = fmaf(x[i], a.y, acc[1]);
@@ -244,7 +306,7 @@ __device__ __forceinline__ void dot_all(const LabelParams& p, const float* __res
         }
     }
     for (; ch < p.F; ++ch) {
-        const float x = __ldg(f + (size_t)ch * P);
+        const float x = f.at(ch);
 #pragma unroll
         for (int g = 0; g < kGroup; ++g) acc[g] = fmaf(x, sproto[(size_t)ch * kGroup + g], acc[g]);
     }
@@ -267,6 +329,7 @@ __device__ __forceinline__ void stage_entries(const LabelParams& p, float* sprot
 
 // ------------------------------------------------------------------------------------------ assign
 // CTA (s, slice): nearest prototype of s for the selected pixels of s in this slice  (:213-230)
+template <typename FT, bool LOWRES>
 __global__ void __launch_bounds__(kAssignThreads) proto_assign_kernel(LabelParams p) {
     extern __shared__ __align__(16) float sproto[];          // [F][kGroup]
     __shared__ ProtoEntry ent[kGroup];
@@ -298,7 +361,7 @@ __global__ void __launch_bounds__(kAssignThreads) proto_assign_kernel(LabelParam
             __syncthreads();
             if (mine) {
                 float acc[kGroup];
-                dot_all(p, sproto, pix, acc);
+                dot_all<FT, LOWRES>(p, sproto, pix, acc);
 #pragma unroll
                 for (int g = 0; g < kGroup; ++g) {
                     if (g < n && (acc[g] > best || bestc == 255)) { best = acc[g]; bestc = ent[g].c; }
@@ -436,6 +499,7 @@ __global__ void __launch_bounds__(kAssignThreads) proto_threshold_kernel(LabelPa
 // selected superpixel (t itself included) whose test "some threshold < similarity" passes  (:276-305, ascending
 // overwrite order == the largest passing id wins).  The prototypes of the neighbours are walked in that order,
 // kGroup at a time; a pixel stops at its first passing neighbour.
+template <typename FT, bool LOWRES>
 __global__ void __launch_bounds__(kAssignThreads) proto_propagate_kernel(LabelParams p) {
     extern __shared__ __align__(16) float sproto[];          // [F][kGroup]
     __shared__ ProtoEntry ent[kGroup];
@@ -501,7 +565,7 @@ __global__ void __launch_bounds__(kAssignThreads) proto_propagate_kernel(LabelPa
             if (all_done) break;
             if (!done) {
                 float acc[kGroup];
-                dot_all(p, sproto, pix, acc);
+                dot_all<FT, LOWRES>(p, sproto, pix, acc);
 #pragma unroll
                 for (int g = 0; g < kGroup; ++g) {
                     if (g < n && !done) {
@@ -566,7 +630,7 @@ size_t zeroed_bytes(int C, int S) {
            align_up(words * 4);
 }
 
-template <typename IdT>
+template <typename IdT, typename FT, bool LOWRES>
 int run_labeller(const LabelParams& p, const Workspace& w, cudaStream_t st) {
     const int threads = 256;
     const unsigned grid_px = (unsigned)std::min<long long>(((long long)p.P + threads - 1) / threads, (long long)mas::sm_count() * 16);
@@ -575,12 +639,12 @@ int run_labeller(const LabelParams& p, const Workspace& w, cudaStream_t st) {
     spx_fill_kernel<IdT><<<grid_px, threads, 0, st>>>(p.ids, p.P, p.S, w.offset, w.cursor, w.pixlist);
     spx_adjacency_kernel<IdT><<<grid_px, threads, 0, st>>>(p.ids, p.H, p.W, p.S, p.words, w.adj);
     const long long entries = (long long)p.S * p.C;
-    proto_gather_kernel<<<(unsigned)((entries * 32 + threads - 1) / threads), threads, 0, st>>>(p);
+    proto_gather_kernel<FT, LOWRES><<<(unsigned)((entries * 32 + threads - 1) / threads), threads, 0, st>>>(p);
     const size_t smem = (size_t)kGroup * p.F * sizeof(float);
     const dim3 grid_sp((unsigned)p.S, kSlices);
-    proto_assign_kernel<<<grid_sp, kAssignThreads, smem, st>>>(p);
+    proto_assign_kernel<FT, LOWRES><<<grid_sp, kAssignThreads, smem, st>>>(p);
     proto_threshold_kernel<<<p.S, kAssignThreads, 0, st>>>(p);
-    proto_propagate_kernel<<<grid_sp, kAssignThreads, smem, st>>>(p);
+    proto_propagate_kernel<FT, LOWRES><<<grid_sp, kAssignThreads, smem, st>>>(p);
     mas::count_launches(8);
     MAS_LAUNCH_OK("prototype labeller kernels");
     return 0;
@@ -615,21 +679,26 @@ extern "C" size_t mas_proto_labeller_workspace_bytes(int feat_channels, int chan
     return carve(nullptr, feat_channels, channels, height, width, nseg).bytes;
 }
 
-extern "C" int mas_proto_labeller_dev(const float* feats, int feat_channels, const float* logits, int channels,
-                                      const uint8_t* targets, int target_channels, const uint8_t* mask, const void* ids,
-                                      int ids_dtype, int height, int width, int nseg, int only_multihot, int threshold_mode,
-                                      uint8_t* labels, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
-    MAS_REQUIRE(feats && logits && targets && mask && ids && labels && status && workspace, MAS_E_BADARG, "proto_labeller: null pointer");
-    MAS_REQUIRE(feat_channels > 0 && height > 0 && width > 0 && nseg > 0, MAS_E_BADARG, "proto_labeller: bad shape");
+namespace {
+
+int proto_labeller_impl(const char* what, const void* feats, int feat_dtype, int feat_channels, int feat_height, int feat_width,
+                        const float* logits, int channels, const uint8_t* targets, int target_channels, const uint8_t* mask,
+                        const void* ids, int ids_dtype, int height, int width, int nseg, int only_multihot, int threshold_mode,
+                        uint8_t* labels, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+    MAS_REQUIRE(feats && logits && targets && mask && ids && labels && status && workspace, MAS_E_BADARG, "%s: null pointer", what);
+    MAS_REQUIRE(feat_channels > 0 && height > 0 && width > 0 && nseg > 0, MAS_E_BADARG, "%s: bad shape", what);
+    MAS_REQUIRE(feat_dtype == MAS_F32 || feat_dtype == MAS_BF16, MAS_E_BADARG, "%s: bad feature dtype", what);
+    MAS_REQUIRE(feat_height > 0 && feat_width > 0 && feat_height <= height && feat_width <= width, MAS_E_BADARG,
+                "%s: the feature map (%d x %d) must not be larger than the image (%d x %d)", what, feat_height, feat_width, height, width);
     MAS_REQUIRE(channels >= 2 && channels <= MAS_MAX_LOSS_CLASSES && channels <= target_channels, MAS_E_RANGE,
-                "proto_labeller: channels=%d must be in [2,%d] and <= target_channels", channels, MAS_MAX_LOSS_CLASSES);
-    MAS_REQUIRE(ids_dtype == MAS_I32 || ids_dtype == MAS_I64, MAS_E_BADARG, "proto_labeller: bad ids dtype");
-    MAS_REQUIRE(threshold_mode == MAS_THRESHOLD_MEDIAN || threshold_mode == MAS_THRESHOLD_MIN, MAS_E_BADARG, "proto_labeller: bad threshold mode");
-    MAS_REQUIRE((long long)height * width < (1ll << 31), MAS_E_RANGE, "proto_labeller: image too large");
-    MAS_REQUIRE((size_t)kGroup * feat_channels * sizeof(float) <= 48 * 1024, MAS_E_RANGE, "proto_labeller: feat_channels too large");
-    MAS_REQUIRE(((uintptr_t)workspace) % 256 == 0, MAS_E_BADARG, "proto_labeller: workspace must be 256-byte aligned");
+                "%s: channels=%d must be in [2,%d] and <= target_channels", what, channels, MAS_MAX_LOSS_CLASSES);
+    MAS_REQUIRE(ids_dtype == MAS_I32 || ids_dtype == MAS_I64, MAS_E_BADARG, "%s: bad ids dtype", what);
+    MAS_REQUIRE(threshold_mode == MAS_THRESHOLD_MEDIAN || threshold_mode == MAS_THRESHOLD_MIN, MAS_E_BADARG, "%s: bad threshold mode", what);
+    MAS_REQUIRE((long long)height * width < (1ll << 31), MAS_E_RANGE, "%s: image too large", what);
+    MAS_REQUIRE((size_t)kGroup * feat_channels * sizeof(float) <= 48 * 1024, MAS_E_RANGE, "%s: feat_channels too large", what);
+    MAS_REQUIRE(((uintptr_t)workspace) % 256 == 0, MAS_E_BADARG, "%s: workspace must be 256-byte aligned", what);
     const Workspace w = carve(workspace, feat_channels, channels, height, width, nseg);
-    MAS_REQUIRE(workspace_bytes >= w.bytes, MAS_E_WORKSPACE, "proto_labeller: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+    MAS_REQUIRE(workspace_bytes >= w.bytes, MAS_E_WORKSPACE, "%s: workspace too small (%zu < %zu)", what, workspace_bytes, w.bytes);
     cudaStream_t st = (cudaStream_t)stream;
     const long long P = (long long)height * width;
 
@@ -648,10 +717,40 @@ extern "C" int mas_proto_labeller_dev(const float* feats, int feat_channels, con
     LabelParams p = {};
     p.feats = feats; p.mask = mask; p.ids = ids;
     p.F = feat_channels; p.C = channels; p.H = height; p.W = width; p.S = nseg; p.P = (int)P;
+    const bool lowres = feat_height != height || feat_width != width;
+    p.fh_in = feat_height; p.fw_in = feat_width;
+    // torch's area_pixel_compute_scale<float>(input, output, align_corners=false): (float)input / output
+    p.fry = (float)feat_height / (float)height; p.frx = (float)feat_width / (float)width;
     p.threshold_min = threshold_mode == MAS_THRESHOLD_MIN;
     p.info = w.info; p.gmax = w.gmax; p.offset = w.offset; p.pixlist = w.pixlist; p.proto = w.proto;
     p.own_sim = w.own_sim; p.own_cls = w.own_cls; p.thr = w.thr; p.adj = w.adj; p.svalid = w.svalid;
     p.words = (nseg + 31) / 32;
     p.labels = labels;
-    return ids_dtype == MAS_I64 ? run_labeller<long long>(p, w, st) : run_labeller<int32_t>(p, w, st);
+    const bool i64 = ids_dtype == MAS_I64, bf16 = feat_dtype == MAS_BF16;
+#define MAS_RUN(IdT)                                                                                                   \
+    (bf16 ? (lowres ? run_labeller<IdT, __nv_bfloat16, true>(p, w, st) : run_labeller<IdT, __nv_bfloat16, false>(p, w, st)) \
+          : (lowres ? run_labeller<IdT, float, true>(p, w, st) : run_labeller<IdT, float, false>(p, w, st)))
+    return i64 ? MAS_RUN(long long) : MAS_RUN(int32_t);
+#undef MAS_RUN
+}
+
+}  // namespace
+
+extern "C" int mas_proto_labeller_dev(const float* feats, int feat_channels, const float* logits, int channels,
+                                      const uint8_t* targets, int target_channels, const uint8_t* mask, const void* ids,
+                                      int ids_dtype, int height, int width, int nseg, int only_multihot, int threshold_mode,
+                                      uint8_t* labels, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+    return proto_labeller_impl("proto_labeller", feats, MAS_F32, feat_channels, height, width, logits, channels, targets, target_channels,
+                               mask, ids, ids_dtype, height, width, nseg, only_multihot, threshold_mode, labels, status, workspace,
+                               workspace_bytes, stream);
+}
+
+extern "C" int mas_proto_labeller_src_dev(const void* feats, int feat_dtype, int feat_channels, int feat_height, int feat_width,
+                                          const float* logits, int channels, const uint8_t* targets, int target_channels,
+                                          const uint8_t* mask, const void* ids, int ids_dtype, int height, int width, int nseg,
+                                          int only_multihot, int threshold_mode, uint8_t* labels, int32_t* status, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+    return proto_labeller_impl("proto_labeller_src", feats, feat_dtype, feat_channels, feat_height, feat_width, logits, channels, targets,
+                               target_channels, mask, ids, ids_dtype, height, width, nseg, only_multihot, threshold_mode, labels, status,
+                               workspace, workspace_bytes, stream);
 }

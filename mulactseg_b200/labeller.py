@@ -8,7 +8,10 @@ Reference (file:line relative to the reference checkout):
       trainer/eval_within_multihot.py:93-146
 ``ProtoLabellerMixin`` / ``TopLabellerMixin`` give a trainer class these methods with the reference's argument
 lists; ``args.cosprop_threshold_method`` ('median' | 'min') and ``args.nseg`` are read like the reference does.
-The VOC multi-scale variant (``..._includeonehot_voc_ms.py``) is out of scope this round.
+The VOC multi-scale variant (``..._includeonehot_voc_ms.py``) calls the same function on fused features
+(``trainer/eval_save_cosplbl_prop_includeonehot_voc_ms.fuse_multiscale``).
+``feats`` may be fp32 or bf16, and either the reference's full-resolution (N,F,H,W) map or -- opt-in -- the head's
+low-resolution (N,F,h,w) map, which the kernels interpolate on the fly.
 """
 from __future__ import annotations
 
@@ -33,7 +36,9 @@ def pseudo_label_generation(labels, feats, inputs, targets, spmasks, superpixels
         raise RuntimeError("mulactseg_b200 labellers need CUDA tensors (there is no CPU path)")
     n = inputs.shape[0]
     trg, mask, spx = _prep(targets, spmasks, superpixels)
-    feats = feats.contiguous().float()
+    # fp32 or bf16 features are read as they are; full resolution (the reference's x4 up-sampled map) or the head's
+    # low-resolution map (interpolated inside the kernels, ``mas_proto_labeller_src_dev``)
+    feats = feats.contiguous() if feats.dtype in (torch.float32, torch.bfloat16) else feats.contiguous().float()
     inputs = inputs.contiguous().float()
     outs, stats = [], []
     for i in range(n):

@@ -448,27 +448,30 @@ def _labeller_workspace(device, fch, c, h, w, nseg) -> torch.Tensor:
 
 def proto_labeller(feats: torch.Tensor, logits: torch.Tensor, targets: torch.Tensor, mask: torch.Tensor, spx: torch.Tensor,
                    only_multihot: bool, threshold: str):
-    """One image: feats (F,H,W) f32, logits (C,H,W) f32, targets (S,Ct) u8, mask (H,W) bool, spx (H,W) i32|i64
-    -> (labels (H,W) uint8, status (1,) int32 on the device).  See ``mas_proto_labeller_dev``."""
-    _want(feats, "feats", torch.float32, 3)
+    """One image: feats (F,H,W) f32|bf16 -- or the head's LOW-RESOLUTION (F,h,w) map, interpolated inside the kernels --,
+    logits (C,H,W) f32, targets (S,Ct) u8, mask (H,W) bool, spx (H,W) i32|i64
+    -> (labels (H,W) uint8, status (1,) int32 on the device).  See ``mas_proto_labeller_src_dev``."""
+    _want(feats, "feats", (torch.float32, torch.bfloat16), 3)
     _want(logits, "inputs", torch.float32, 3)
     _want(targets, "targets", torch.uint8, 2)
     _want(mask, "spmasks", (torch.bool, torch.uint8), 2)
     _want(spx, "superpixels", (torch.int32, torch.int64), 2)
-    fch, h, w = feats.shape
-    c = logits.shape[0]
+    fch, fh, fw = feats.shape
+    c, h, w = logits.shape
     nseg, ct = targets.shape
-    if tuple(logits.shape[1:]) != (h, w) or tuple(mask.shape) != (h, w) or tuple(spx.shape) != (h, w):
-        raise RuntimeError("feats / inputs / spmasks / superpixels spatial shapes differ")
+    if tuple(mask.shape) != (h, w) or tuple(spx.shape) != (h, w):
+        raise RuntimeError("inputs / spmasks / superpixels spatial shapes differ")
+    if fh > h or fw > w:
+        raise RuntimeError(f"feats ({fh}x{fw}) larger than the image ({h}x{w})")
     if threshold not in ("median", "min"):
         raise NotImplementedError(f"cosprop_threshold_method={threshold!r}")
     labels = torch.empty((h, w), dtype=torch.uint8, device=feats.device)
     status = torch.zeros(1, dtype=torch.int32, device=feats.device)
     ws = _labeller_workspace(feats.device, fch, c, h, w, nseg)
     with _on(feats):
-        _lib.call("mas_proto_labeller_dev", feats.data_ptr(), fch, logits.data_ptr(), c, targets.data_ptr(), ct,
-                  mask.data_ptr(), spx.data_ptr(), _ids_dtype(spx), h, w, nseg, int(bool(only_multihot)),
-                  _lib.MAS_THRESHOLD_MEDIAN if threshold == "median" else _lib.MAS_THRESHOLD_MIN,
+        _lib.call("mas_proto_labeller_src_dev", feats.data_ptr(), _lib.MAS_F32 if feats.dtype == torch.float32 else _lib.MAS_BF16,
+                  fch, fh, fw, logits.data_ptr(), c, targets.data_ptr(), ct, mask.data_ptr(), spx.data_ptr(), _ids_dtype(spx), h, w,
+                  nseg, int(bool(only_multihot)), _lib.MAS_THRESHOLD_MEDIAN if threshold == "median" else _lib.MAS_THRESHOLD_MIN,
                   labels.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), _stream(feats))
     return labels, status
 

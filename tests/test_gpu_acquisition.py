@@ -469,19 +469,24 @@ def test_lowres_entry_matches_oracle_on_the_interpolated_logits(shape):
     for i in range(0, n, 2):
         stats.add_batch_lowres(i, x[i:i + 2], ids[i:i + 2], 0.1)
     score, _ = acq.finalize(stats, spec, 6.0, 2)
-    # interpolated logits of neighbouring classes can come within an ulp of each other, where our interpolation (same
-    # expression as torch's CUDA kernel) and torch's CPU kernel may round differently and flip an arg-max: compare the
-    # histograms on pixels whose top-2 gap exceeds the rounding, the scores at the north_star tolerance
+    # Where the two largest interpolated logits of a pixel (nearly) coincide the arg-max is not defined across
+    # implementations: border pixels copy a single tap (bf16 sources tie exactly there; torch's topk order among equal
+    # probabilities is arbitrary), and an ulp of difference between this kernel's interpolation and torch's CPU kernel can
+    # flip a near-tie.  Regions holding such a pixel are left out; everything else is held to the north_star tolerance.
     top2 = full.topk(2, dim=1).values
-    safe = (top2[:, 0] - top2[:, 1]) > 1e-5
+    unsafe_px = (top2[:, 0] - top2[:, 1]) <= 1e-5
+    unsafe = torch.zeros((n, nseg + 1), dtype=torch.bool)
+    for i in range(n):
+        unsafe[i, spx[i][unsafe_px[i]].clamp(max=nseg)] = True
+    safe = ~unsafe[:, :nseg].numpy()
+    assert safe.mean() > 0.7
     cnt = stats.cls_cnt.cpu().long()
     assert cnt.sum(dim=(1, 2)).tolist() == [int((spx[i] < nseg).sum()) for i in range(n)]
-    if bool(safe.all()):
-        np.testing.assert_array_equal(cnt.numpy(), oa.region_histograms(pool, nseg, 0.1).numpy())
-    assert_scores_close(score.cpu().numpy(), ref.numpy(), False, str(shape))
+    np.testing.assert_array_equal(cnt.numpy()[safe], oa.region_histograms(pool, nseg, 0.1).numpy()[safe])
+    assert_scores_close(score.cpu().numpy()[safe], ref.numpy()[safe], False, str(shape))
     # and equal to our own full-resolution kernels on the interpolated tensor (same tolerance, independent path)
     stats_full = acq.RegionStats(n, nseg, c, DEV, need_prob=True)
     stats_full.add_batch(0, full.to(DEV), ids, 0.1)
     score_full, _ = acq.finalize(stats_full, spec, 6.0, 2)
-    np.testing.assert_allclose(score.cpu().numpy(), score_full.cpu().numpy(), rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(score.cpu().numpy()[safe], score_full.cpu().numpy()[safe], rtol=1e-5, atol=1e-12)
     np.testing.assert_allclose(stats.prob_sum.cpu().numpy(), stats_full.prob_sum.cpu().numpy(), rtol=1e-5)

@@ -68,6 +68,36 @@ def test_proto_labeller_matches_oracle(shape, only_multihot, thr):
     assert mismatch == 0, f"{mismatch} of {h * w} pixels differ"
 
 
+@pytest.mark.parametrize("shape", [(64, 96, 40, 12, 64, 0.3, 4), (40, 56, 20, 7, 32, 0.5, 4), (129, 129, 30, 21, 48, 0.4, 0)])
+@pytest.mark.parametrize("source", ["lowres_f32", "lowres_bf16", "full_bf16"])
+def test_feature_sources_match_oracle(shape, source):
+    """mas_proto_labeller_src_dev: bf16 features, and the head's LOW-RESOLUTION features interpolated inside the kernels
+     -- labels must equal the oracle run on what the reference would have been handed: the
+    F.interpolate(..., mode='bilinear', align_corners=False) of the same map, in fp32 (models/segmentation/utils.py:28-34)."""
+    from mulactseg_b200 import labeller
+    h, w, nseg, c, ch, rho, stride = shape
+    g = torch.Generator().manual_seed(h * w + ch)
+    hl, wl = (h // stride, w // stride) if stride else (33, 33)          # 33 -> 129: the VOC ratio (513 = 129 * 3.977)
+    low = torch.nn.functional.normalize(torch.randn((1, ch, hl, wl), generator=g), dim=1)
+    if source == "lowres_bf16":
+        low = low.to(torch.bfloat16)
+    full = torch.nn.functional.interpolate(low.float(), size=(h, w), mode="bilinear", align_corners=False)
+    if source == "full_bf16":
+        full = full.to(torch.bfloat16)
+    logits = synth.logits(1, c, h, w, "normal", seed=w, coherent=4)
+    spx = synth.superpixel_map(1, h, w, nseg, "jitter", seed=nseg)
+    trg = synth.multihot_targets(1, nseg, c, seed=c, p_extra=0.3)
+    mask = synth.region_mask(spx, nseg, rho, seed=ch)
+    ref = ol.pseudo_label_generation(full.float(), logits, trg, mask, spx)
+    feats = full if source == "full_bf16" else low
+    got = labeller.pseudo_label_generation(None, feats.to(DEV), logits.to(DEV), trg.to(DEV), mask.to(DEV), spx.to(DEV)).cpu()
+    # low-resolution sources: the interpolation is evaluated with the expression of torch's CUDA kernel, the oracle's
+    # features come from torch's CPU kernel -- an ulp apart at most, which can flip a pixel only where two similarities
+    # (or a similarity and its threshold) agree to rounding
+    assert int((got != ref).sum()) <= (0 if source == "full_bf16" else 1)
+    assert float((ref != 255).float().mean()) > 0.05
+
+
 def test_voc_multiscale_variant_matches_oracle():
     """..._includeonehot_voc_ms.py: features averaged over scales (+ flipped copies) and re-normalised, then the same
     pseudo_label_generation; VOC-shaped (21 classes, ~150 superpixels)."""
