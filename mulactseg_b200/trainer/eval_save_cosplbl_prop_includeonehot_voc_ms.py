@@ -37,3 +37,9 @@ def fuse_multiscale(feat_list: Sequence[torch.Tensor], output_list: Sequence[tor
 class LabellerMixin(ProtoLabellerMixin):
     only_multihot = False
     fuse_multiscale = staticmethod(fuse_multiscale)
+
+
+from ._bind import bind  # noqa: E402
+
+# the reference's own trainer with the hot-path methods replaced (None when the reference checkout is not importable)
+ActiveTrainer = bind("eval_save_cosplbl_prop_includeonehot_voc_ms", LabellerMixin, "trainer/eval_save_cosplbl_prop_includeonehot_voc_ms.py with the fused pseudo_label_generation (:152-354).")

@@ -90,8 +90,48 @@ def low_res(res, c, dtype):
         print(k, res[k], flush=True)
 
 
+def labeller_sources(res):
+    """Prototype labeller, one Cityscapes-shaped image: feature sources side by side."""
+    from mulactseg_b200 import labeller
+    h, w, nseg, c, rho = 1024, 2048, 2048, 20, 0.08
+    lows = [torch.nn.functional.normalize(torch.randn((1, 256, h // 4, w // 4), device=DEV,
+                                                       generator=torch.Generator(device=DEV).manual_seed(i)), dim=1) for i in range(4)]
+    logits = [synth.logits(1, c, h, w, "normal", seed=30 + i, device=DEV, coherent=4) for i in range(4)]
+    spx = synth.superpixel_map(1, h, w, nseg, "jitter", seed=3, device=DEV)
+    trg = synth.multihot_targets(1, nseg, c, seed=4, device=DEV, p_ignore=0.0)
+    mask = synth.region_mask(spx, nseg, rho, seed=5)
+    for name in ("full f32", "full bf16", "lowres f32", "lowres bf16", "F.interpolate + full f32"):
+        if name.startswith("full"):
+            feats = [torch.nn.functional.interpolate(x, size=(h, w), mode="bilinear", align_corners=False) for x in lows]
+            if "bf16" in name:
+                feats = [f.to(torch.bfloat16) for f in feats]
+        else:
+            feats = [x.to(torch.bfloat16) if "bf16" in name else x for x in lows]
+
+        def run(i):
+            f = feats[i % 4]
+            if name.startswith("F.interpolate"):
+                f = torch.nn.functional.interpolate(f, size=(h, w), mode="bilinear", align_corners=False)
+            labeller.pseudo_label_generation(None, f, logits[i % 4], trg, mask, spx, check=False)
+
+        ms = time_ms(run, iters=12)
+        res[f"labeller cityscapes feats={name}"] = {"ms_per_image": round(ms, 4)}
+        print(f"labeller cityscapes feats={name}", res[f"labeller cityscapes feats={name}"], flush=True)
+        del feats
+
+
 def main():
     res = {}
+    if "labeller" in sys.argv[1:]:
+        labeller_sources(res)
+        print(json.dumps(res, indent=1))
+        return
+    if "voc513" in sys.argv[1:]:          # short: for ncu
+        full_res(res, "voc_crop 513x513x22", 22, 513, 513, 150, 64, ["default"])
+        return
+    if "lowres" in sys.argv[1:]:
+        low_res(res, 19, torch.float32)
+        return
     full_res(res, "voc_crop 513x513x22", 22, 513, 513, 150, 512, ["ldg", "default"])
     full_res(res, "voc_native 375x500x22", 22, 375, 500, 150, 512, ["default", "abreast", "ldg"])
     full_res(res, "cityscapes 1024x2048x19", 19, 1024, 2048, 2048, 48, ["default", "abreast"])
