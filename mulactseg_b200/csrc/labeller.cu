@@ -39,6 +39,8 @@ struct LabelParams {
     const void* ids;        // (H, W)
     int F, C, H, W, S, P;
     int threshold_min;      // 0: lower median, 1: min
+    int only_multihot;
+    int32_t* status;
     const uint32_t* info;               // (S)
     const unsigned long long* gmax;     // (S, C)
     const int* offset;                  // (S + 1) CSR offsets
@@ -49,6 +51,7 @@ struct LabelParams {
     float* thr;                         // (S, C)
     uint32_t* adj;                      // (S, words)
     uint32_t* svalid;                   // (words) selected superpixels that own prototypes
+    uint8_t* touched;                   // (S) 1: the superpixel or one of its 8-neighbours owns prototypes
     int words;
     uint8_t* labels;                    // (H, W)
 };
@@ -159,23 +162,43 @@ __device__ __forceinline__ void run_info(int id, int lane, int& head_lane, int& 
     run_len = next - head_lane;
 }
 
+__device__ __forceinline__ void adj_set(uint32_t* adj, int words, int a, int b);
+
+// pixels per superpixel (warp-aggregated runs) and, in the same pass over the id map, the adjacency bit matrix of the
+// 3x3 dilation (:260-266): every 8-neighbour pair is seen once from its upper / left pixel
 template <typename IdT>
-__global__ void spx_count_kernel(const void* __restrict__ ids, int P, int S, int* __restrict__ count) {
+__global__ void spx_count_adjacency_kernel(const void* __restrict__ ids, int H, int W, int S, int* __restrict__ count, int words,
+                                           uint32_t* __restrict__ adj) {
     const int lane = threadIdx.x & 31;
-    const long long padded = ((long long)P + 31) & ~31ll;
+    const long long P = (long long)H * W;
+    const long long padded = (P + 31) & ~31ll;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += (long long)gridDim.x * blockDim.x) {
         const int id = i < P ? read_id<IdT>(ids, (size_t)i, S) : -1;
         int head_lane, run_len;
         run_info(id, lane, head_lane, run_len);
         if (lane == head_lane && id >= 0) atomicAdd(count + id, run_len);
+        if (id < 0) continue;
+        const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+        const int dx[4] = {1, -1, 0, 1}, dy[4] = {0, 1, 1, 1};      // right, down-left, down, down-right
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xx = x + dx[k], yy = y + dy[k];
+            if (xx < 0 || xx >= W || yy >= H) continue;
+            const int b = read_id<IdT>(ids, (size_t)yy * W + xx, S);
+            if (b < 0 || b == id) continue;
+            adj_set(adj, words, id, b);
+            adj_set(adj, words, b, id);
+        }
     }
 }
 
 // exclusive scan of count[0..S) into offset[0..S]; also clears the fill cursors
-__global__ void spx_scan_kernel(const int* __restrict__ count, int S, int* __restrict__ offset, int* __restrict__ cursor) {
+__global__ void spx_scan_kernel(const int* __restrict__ count, int S, int* __restrict__ offset, int* __restrict__ cursor,
+                                const double* __restrict__ acc, int only_multihot, int32_t* __restrict__ status) {
     __shared__ int warp_sums[32];
     __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
+    // status: selected pixels whose superpixel has no candidate class (the reference fails on such input, :226)
+    if (threadIdx.x == 0) { carry = 0; status[0] = only_multihot ? 0 : (int32_t)acc[5]; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int base = 0; base < S; base += blockDim.x) {
@@ -231,27 +254,6 @@ __device__ __forceinline__ void adj_set(uint32_t* adj, int words, int a, int b) 
     if (!(*reinterpret_cast<volatile uint32_t*>(w) & bit)) atomicOr(w, bit);
 }
 
-template <typename IdT>
-__global__ void spx_adjacency_kernel(const void* __restrict__ ids, int H, int W, int S, int words, uint32_t* adj) {
-    const long long P = (long long)H * W;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
-        const int y = (int)(i / W), x = (int)(i - (long long)y * W);
-        const int a = read_id<IdT>(ids, (size_t)i, S);
-        if (a < 0) continue;
-        // right, down-left, down, down-right: every 8-neighbour pair is seen once
-        const int dx[4] = {1, -1, 0, 1}, dy[4] = {0, 1, 1, 1};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int xx = x + dx[k], yy = y + dy[k];
-            if (xx < 0 || xx >= W || yy >= H) continue;
-            const int b = read_id<IdT>(ids, (size_t)yy * W + xx, S);
-            if (b < 0 || b == a) continue;
-            adj_set(adj, words, a, b);
-            adj_set(adj, words, b, a);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------ prototypes
 // one warp per (superpixel, class): copy the feature column of the arg-max-probability pixel
 template <typename FT, bool LOWRES>
@@ -284,8 +286,10 @@ constexpr int kSlices = 4;         // CTAs that share the pixels of one superpix
 
 // sproto layout: [channel][kGroup] so that the kGroup operands of one channel are two 128-bit broadcast reads
 // (a 4-prototype instantiation for sparse batches was measured slower: the compiler keeps fewer loads in flight)
-template <typename FT, bool LOWRES>
-__device__ __forceinline__ void dot_all(const LabelParams& p, const float* __restrict__ sproto, int pix, float (&acc)[kGroup]) {
+// G = 8: all kGroup slots; G = 4: only the first four (most batches hold <= 4 prototypes -- half the FMAs and shared-memory
+// reads).  A slot's similarity is the same FMA chain either way.
+template <typename FT, bool LOWRES, int G>
+__device__ __forceinline__ void dot_some(const LabelParams& p, const float* __restrict__ sproto, int pix, float (&acc)[kGroup]) {
 #pragma unroll
     for (int g = 0; g < kGroup; ++g) acc[g] = 0.f;
     const FeatColumn<FT, LOWRES> f(p, pix);
@@ -298,18 +302,27 @@ __device__ __forceinline__ void dot_all(const LabelParams& p, const float* __res
 #pragma unroll
         for (int i = 0; i < kBatch; ++i) {
             const float4 a = *reinterpret_cast<const float4*>(sproto + (size_t)(ch + i) * kGroup);
-            const float4 b = *reinterpret_cast<const float4*>(sproto + (size_t)(ch + i) * kGroup + 4);
             acc[0] = fmaf(x[i], a.x, acc[0]); acc[1] = fmaf(x[i], a.y, acc[1]);
             acc[2] = fmaf(x[i], a.z, acc[2]); acc[3] = fmaf(x[i], a.w, acc[3]);
-            acc[4] = fmaf(x[i], b.x, acc[4]); acc[5] = fmaf(x[i], b.y, acc[5]);
-            acc[6] = fmaf(x[i], b.z, acc[6]); acc[7] = fmaf(x[i], b.w, acc[7]);
+            if (G > 4) {
+                const float4 b = *reinterpret_cast<const float4*>(sproto + (size_t)(ch + i) * kGroup + 4);
+                acc[4] = fmaf(x[i], b.x, acc[4]); acc[5] = fmaf(x[i], b.y, acc[5]);
+                acc[6] = fmaf(x[i], b.z, acc[6]); acc[7] = fmaf(x[i], b.w, acc[7]);
+            }
         }
     }
     for (; ch < p.F; ++ch) {
         const float x = f.at(ch);
 #pragma unroll
-        for (int g = 0; g < kGroup; ++g) acc[g] = fmaf(x, sproto[(size_t)ch * kGroup + g], acc[g]);
+        for (int g = 0; g < G; ++g) acc[g] = fmaf(x, sproto[(size_t)ch * kGroup + g], acc[g]);
     }
+}
+
+// n = prototypes staged in sproto (warp-uniform)
+template <typename FT, bool LOWRES>
+__device__ __forceinline__ void dot_all(const LabelParams& p, const float* __restrict__ sproto, int pix, int n, float (&acc)[kGroup]) {
+    if (n <= 4) dot_some<FT, LOWRES, 4>(p, sproto, pix, acc);
+    else dot_some<FT, LOWRES, 8>(p, sproto, pix, acc);
 }
 static_assert(kGroup == 8, "dot_all is written for 8 prototypes per pass");
 
@@ -361,7 +374,7 @@ __global__ void __launch_bounds__(kAssignThreads) proto_assign_kernel(LabelParam
             __syncthreads();
             if (mine) {
                 float acc[kGroup];
-                dot_all<FT, LOWRES>(p, sproto, pix, acc);
+                dot_all<FT, LOWRES>(p, sproto, pix, n, acc);
 #pragma unroll
                 for (int g = 0; g < kGroup; ++g) {
                     if (g < n && (acc[g] > best || bestc == 255)) { best = acc[g]; bestc = ent[g].c; }
@@ -387,6 +400,15 @@ __global__ void __launch_bounds__(kAssignThreads) proto_threshold_kernel(LabelPa
     __shared__ unsigned int sel_prefix, sel_rank;
     __shared__ float red[kAssignThreads / 32];
     const int s = blockIdx.x;
+    if (threadIdx.x < 32) {
+        // does s or any superpixel adjacent to it own prototypes?  The propagate CTAs of all other superpixels -- half the
+        // image at rho = 0.08 -- then leave after one load instead of scanning the adjacency row in every thread.
+        const uint32_t* row = p.adj + (size_t)s * p.words;
+        bool any = false;
+        for (int w = threadIdx.x; w < p.words; w += 32) any |= ((row[w] | ((w == (s >> 5)) ? (1u << (s & 31)) : 0u)) & p.svalid[w]) != 0u;
+        any = __any_sync(0xffffffffu, any);
+        if (threadIdx.x == 0) p.touched[s] = any ? 1 : 0;
+    }
     if (!((p.svalid[s >> 5] >> (s & 31)) & 1u)) return;
     const uint32_t inf = p.info[s];
     const uint32_t bits = inf & ~kGroupBit;
@@ -509,11 +531,8 @@ __global__ void __launch_bounds__(kAssignThreads) proto_propagate_kernel(LabelPa
     const int t = blockIdx.x;
     const int beg = p.offset[t], end = p.offset[t + 1];
     if (beg + (int)blockIdx.y * kAssignThreads >= end) return;
+    if (!p.touched[t]) return;                                // no selected neighbour at all (spx_touch_kernel)
     const uint32_t* row = p.adj + (size_t)t * p.words;
-    // any selected neighbour at all?
-    bool any = false;
-    for (int w = 0; w < p.words && !any; ++w) any = ((row[w] | ((w == (t >> 5)) ? (1u << (t & 31)) : 0u)) & p.svalid[w]) != 0u;
-    if (!any) return;
     const uint32_t inf_t = p.info[t];
 
     for (int base = beg + blockIdx.y * kAssignThreads; base < end; base += kSlices * kAssignThreads) {
@@ -565,7 +584,7 @@ __global__ void __launch_bounds__(kAssignThreads) proto_propagate_kernel(LabelPa
             if (all_done) break;
             if (!done) {
                 float acc[kGroup];
-                dot_all<FT, LOWRES>(p, sproto, pix, acc);
+                dot_all<FT, LOWRES>(p, sproto, pix, n, acc);
 #pragma unroll
                 for (int g = 0; g < kGroup; ++g) {
                     if (g < n && !done) {
@@ -585,15 +604,38 @@ __global__ void __launch_bounds__(kAssignThreads) proto_propagate_kernel(LabelPa
     }
 }
 
-__global__ void labeller_status_kernel(const double* acc, int only_multihot, int32_t* status) {
-    status[0] = only_multihot ? 0 : (int32_t)acc[5];   // selected pixels whose superpixel has no candidate class
+// one launch instead of two memsets + the candidate-word kernel: zero the accumulating part of the workspace, fill the
+// label map with 255 ("unlabeled") and build the candidate word of every superpixel (bit c: class c is a candidate of
+// the net's C channels; top bit: the superpixel takes part -- always, or only when multi-hot; same as mas_multihot_info_dev)
+__global__ void labeller_init_kernel(uint4* __restrict__ zero, size_t zero_vecs, uint8_t* __restrict__ labels, size_t P,
+                                     const uint8_t* __restrict__ targets, int S, int Ct, int C, int only_multihot,
+                                     uint32_t* __restrict__ info) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < zero_vecs; i += stride) zero[i] = make_uint4(0u, 0u, 0u, 0u);
+    const size_t head = min(P, (size_t)((16 - (reinterpret_cast<uintptr_t>(labels) & 15)) & 15));
+    const size_t vecs = (P - head) / 16;
+    uint4* lab16 = reinterpret_cast<uint4*>(labels + head);
+    for (size_t i = tid; i < vecs; i += stride) lab16[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    for (size_t i = tid; i < head; i += stride) labels[i] = 255;
+    for (size_t i = head + vecs * 16 + tid; i < P; i += stride) labels[i] = 255;
+    for (size_t r = tid; r < (size_t)S; r += stride) {
+        const uint8_t* t = targets + r * Ct;
+        uint32_t bits = 0u;
+        int total = 0;
+        for (int c = 0; c < Ct; ++c) {
+            const int v = t[c];
+            total += v;
+            if (c < C && v) bits |= 1u << c;
+        }
+        info[r] = bits | ((!only_multihot || total > 1) ? kGroupBit : 0u);
+    }
 }
 
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Workspace {
     uint32_t* info; unsigned long long* gmax; double* acc; int* count; int* offset; int* cursor; int* pixlist;
-    float* proto; float* own_sim; uint8_t* own_cls; float* thr; uint32_t* adj; uint32_t* svalid;
+    float* proto; float* own_sim; uint8_t* own_cls; float* thr; uint32_t* adj; uint32_t* svalid; uint8_t* touched;
     size_t bytes;
 };
 
@@ -619,6 +661,7 @@ Workspace carve(void* base, int F, int C, int H, int W, int S) {
     w.own_sim = reinterpret_cast<float*>(take(P * 4));
     w.own_cls = reinterpret_cast<uint8_t*>(take(P));
     w.thr = reinterpret_cast<float*>(take((size_t)S * C * 4));
+    w.touched = reinterpret_cast<uint8_t*>(take((size_t)S));
     w.bytes = off;
     (void)zeroed;
     return w;
@@ -634,10 +677,9 @@ template <typename IdT, typename FT, bool LOWRES>
 int run_labeller(const LabelParams& p, const Workspace& w, cudaStream_t st) {
     const int threads = 256;
     const unsigned grid_px = (unsigned)std::min<long long>(((long long)p.P + threads - 1) / threads, (long long)mas::sm_count() * 16);
-    spx_count_kernel<IdT><<<grid_px, threads, 0, st>>>(p.ids, p.P, p.S, w.count);
-    spx_scan_kernel<<<1, 1024, 0, st>>>(w.count, p.S, w.offset, w.cursor);
+    spx_count_adjacency_kernel<IdT><<<grid_px, threads, 0, st>>>(p.ids, p.H, p.W, p.S, w.count, p.words, w.adj);
+    spx_scan_kernel<<<1, 1024, 0, st>>>(w.count, p.S, w.offset, w.cursor, w.acc, p.only_multihot, p.status);
     spx_fill_kernel<IdT><<<grid_px, threads, 0, st>>>(p.ids, p.P, p.S, w.offset, w.cursor, w.pixlist);
-    spx_adjacency_kernel<IdT><<<grid_px, threads, 0, st>>>(p.ids, p.H, p.W, p.S, p.words, w.adj);
     const long long entries = (long long)p.S * p.C;
     proto_gather_kernel<FT, LOWRES><<<(unsigned)((entries * 32 + threads - 1) / threads), threads, 0, st>>>(p);
     const size_t smem = (size_t)kGroup * p.F * sizeof(float);
@@ -645,7 +687,7 @@ int run_labeller(const LabelParams& p, const Workspace& w, cudaStream_t st) {
     proto_assign_kernel<FT, LOWRES><<<grid_sp, kAssignThreads, smem, st>>>(p);
     proto_threshold_kernel<<<p.S, kAssignThreads, 0, st>>>(p);
     proto_propagate_kernel<FT, LOWRES><<<grid_sp, kAssignThreads, smem, st>>>(p);
-    mas::count_launches(8);
+    mas::count_launches(7);
     MAS_LAUNCH_OK("prototype labeller kernels");
     return 0;
 }
@@ -702,17 +744,20 @@ int proto_labeller_impl(const char* what, const void* feats, int feat_dtype, int
     cudaStream_t st = (cudaStream_t)stream;
     const long long P = (long long)height * width;
 
-    MAS_CUDA_OK(cudaMemsetAsync(workspace, 0, zeroed_bytes(channels, nseg), st));
-    MAS_CUDA_OK(cudaMemsetAsync(labels, 0xFF, (size_t)P, st));
-    // candidate words; arg-max-probability pixel per (superpixel, candidate class): softmax with T = 1 (:140)
-    int rc = mas_multihot_info_dev(targets, nseg, target_channels, channels, only_multihot ? MAS_GROUP_ONLYMULTI : MAS_GROUP_ALL,
-                                   w.info, stream);
+    {
+        const size_t zero_vecs = zeroed_bytes(channels, nseg) / 16;       // every carved block is 256-byte aligned
+        const size_t work = std::max<size_t>(std::max<size_t>(zero_vecs, (size_t)P / 16), (size_t)nseg);
+        const unsigned blocks = (unsigned)std::min<size_t>((work + 255) / 256, (size_t)mas::sm_count() * 8);
+        labeller_init_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(workspace), zero_vecs, labels, (size_t)P, targets, nseg,
+                                                     target_channels, channels, only_multihot, w.info);
+        mas::count_launches(1);
+        MAS_LAUNCH_OK("labeller_init_kernel");
+    }
+    // arg-max-probability pixel per (superpixel, candidate class): softmax with T = 1 (:140); the group loss itself is not needed
+    int rc = mas::multihot_loss_fwd(logits, ids, ids_dtype, mask, w.info, 1, channels, height, width, nseg, 1.0f,
+                                    MAS_LOSS_CHOICE | MAS_LOSS_GROUP | MAS_LOSS_EXACT_SOFTMAX, w.acc, reinterpret_cast<uint64_t*>(w.gmax),
+                                    false, stream);
     if (rc != 0) return rc;
-    rc = mas_multihot_loss_fwd_dev(logits, ids, ids_dtype, mask, w.info, 1, channels, height, width, nseg, 1.0f,
-                                   MAS_LOSS_CHOICE | MAS_LOSS_GROUP | MAS_LOSS_EXACT_SOFTMAX, w.acc, reinterpret_cast<uint64_t*>(w.gmax), stream);
-    if (rc != 0) return rc;
-    labeller_status_kernel<<<1, 1, 0, st>>>(w.acc, only_multihot, status);
-    mas::count_launches(1);
 
     LabelParams p = {};
     p.feats = feats; p.mask = mask; p.ids = ids;
@@ -722,8 +767,9 @@ int proto_labeller_impl(const char* what, const void* feats, int feat_dtype, int
     // torch's area_pixel_compute_scale<float>(input, output, align_corners=false): (float)input / output
     p.fry = (float)feat_height / (float)height; p.frx = (float)feat_width / (float)width;
     p.threshold_min = threshold_mode == MAS_THRESHOLD_MIN;
+    p.only_multihot = only_multihot; p.status = status;
     p.info = w.info; p.gmax = w.gmax; p.offset = w.offset; p.pixlist = w.pixlist; p.proto = w.proto;
-    p.own_sim = w.own_sim; p.own_cls = w.own_cls; p.thr = w.thr; p.adj = w.adj; p.svalid = w.svalid;
+    p.own_sim = w.own_sim; p.own_cls = w.own_cls; p.thr = w.thr; p.adj = w.adj; p.svalid = w.svalid; p.touched = w.touched;
     p.words = (nseg + 31) / 32;
     p.labels = labels;
     const bool i64 = ids_dtype == MAS_I64, bf16 = feat_dtype == MAS_BF16;

@@ -627,9 +627,23 @@ extern "C" int mas_multihot_info_dev(const uint8_t* targets, int64_t n_regions, 
     return 0;
 }
 
+namespace mas {
+// forward pass with the group-loss reduction optional: the stage-2 labeller only needs the packed maxima (arg-max pixels)
+int multihot_loss_fwd(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask, const uint32_t* info, int n_img,
+                      int channels, int height, int width, int nseg, float temperature, int flags, double* acc,
+                      uint64_t* group_max, bool reduce_group, void* stream);
+}  // namespace mas
+
 extern "C" int mas_multihot_loss_fwd_dev(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask,
                                          const uint32_t* info, int n_img, int channels, int height, int width, int nseg,
                                          float temperature, int flags, double* acc, uint64_t* group_max, void* stream) {
+    return mas::multihot_loss_fwd(logits, ids, ids_dtype, mask, info, n_img, channels, height, width, nseg, temperature, flags, acc,
+                                  group_max, true, stream);
+}
+
+int mas::multihot_loss_fwd(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask, const uint32_t* info, int n_img,
+                           int channels, int height, int width, int nseg, float temperature, int flags, double* acc,
+                           uint64_t* group_max, bool reduce_group, void* stream) {
     int rc = check_common("multihot_loss_fwd", logits, ids, ids_dtype, mask, info, n_img, channels, height, width, nseg, temperature, flags);
     if (rc != 0) return rc;
     MAS_REQUIRE(acc, MAS_E_BADARG, "multihot_loss_fwd: null acc");
@@ -644,7 +658,7 @@ extern "C" int mas_multihot_loss_fwd_dev(const float* logits, const void* ids, i
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = dispatch(p, ids_dtype, false, (flags & MAS_LOSS_EXACT_SOFTMAX) != 0, st);
     if (e != cudaSuccess) return mas::cuda_fail(e, "multihot_loss_fwd_kernel launch");
-    if (p.do_group) {
+    if (p.do_group && reduce_group) {
         const long long n_regions = (long long)n_img * nseg;
         const int threads = 256;
         const long long blocks = std::min<long long>((n_regions + threads - 1) / threads, (long long)mas::sm_count() * 4);

@@ -1,6 +1,8 @@
 // Abreast / low-resolution path of the fused scorer (see scorer.cu for the overall design).
 #include "scorer.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 using namespace mas_scorer;
@@ -13,14 +15,14 @@ namespace {
 // sectors, and when the warps of a CTA walk strips that are far apart the straddled sectors are fetched twice.  Here the
 // kAbreast warps of a CTA walk ADJACENT strips at the SAME row: what one warp's segment leaves of a sector, its
 // neighbour consumes within the same few hundred cycles (L1 / L2 hit).  Work units are (image, group of kAbreast
-// strips, y), cut into one contiguous range per CTA.  Two lanes per warp prefetch the lines of the row kAhead units
+// strips, y), cut into one contiguous range per CTA.  Two lanes per warp prefetch the lines of the row `ahead` units
 // ahead into L1 (no registers held), so the register loads of a row find their data on chip.
 //
 // The same kernel serves the LOW-RESOLUTION source (LOWRES): the C' planes hold the network head's h_in x w_in logits and
 // every full-resolution value is produced on the fly as F.interpolate(mode='bilinear', align_corners=False) would
 // (models/segmentation/utils.py:28-34) -- the 16x larger tensor is never written or read.
 constexpr int kAbreast = 4;
-constexpr int kAhead = 2;
+constexpr int kAheadDefault = 0;     // rows prefetched ahead into L1 (MAS_SCORER_AHEAD overrides): measured on 513x513x22, 0 -> 3.75 TB/s, 2 -> 3.54, 4 -> 3.07 (line-granular prefetch over-fetches)
 
 template <typename T>
 __device__ __forceinline__ float load_lowres(const T* p);
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(kAbreast * 32) bvsb_stats_abreast_kernel(const
     w.img_region = (long long)at.img * p.S;
     int x0 = ((at.strip * kAbreast + warp) * 32 + lane) * VEC;
     // LOWRES: the horizontal taps depend on the column only -- constant while the warp walks down its strip
+    const bool quad = LOWRES && p.W == 4 * p.w_in;         // exact x4 up-sampling: three column loads serve four pixels
     int cx[VEC], cstep[VEC];
     float cl1[VEC];
     auto column_taps = [&]() {
@@ -104,10 +107,11 @@ __global__ void __launch_bounds__(kAbreast * 32) bvsb_stats_abreast_kernel(const
             }
         }
     };
-    for (int k = 1; k <= kAhead; ++k) prefetch_row(at.y + k);
+    const int ahead = p.stages;
+    for (int k = 1; k <= ahead; ++k) prefetch_row(at.y + k);
 
     for (long long r = r0; r < r1; ++r) {
-        prefetch_row(at.y + kAhead + 1 <= p.H ? at.y + kAhead : p.H);
+        if (ahead > 0) prefetch_row(at.y + ahead);
         if (x0 < p.W) {
             const size_t off = (size_t)at.y * p.W + x0;
             int id[VEC];
@@ -125,6 +129,32 @@ __global__ void __launch_bounds__(kAbreast * 32) bvsb_stats_abreast_kernel(const
                 const float l0y = 1.f - l1y;
                 const T* row0 = img_logits + (size_t)y0i * p.w_in;
                 const size_t down = (size_t)ystep * p.w_in;
+                if (VEC == 4 && quad) {
+                    // exact x4 (the DeepLab head: 256x512 -> 1024x2048): the thread's four pixels x0 = 4k .. 4k+3 read the
+                    // low-resolution columns k-1, k (pixels 0, 1) and k, k+1 (pixels 2, 3).  Three loads per row serve all
+                    // four pixels; at the borders the clamped column repeats its neighbour, which is what torch's taps do
+                    // (left: src clamps to 0 => weight 0 on the repeated value; right: step 0 => the same element twice).
+                    const int k = x0 >> 2;
+                    const int ka = max(k - 1, 0) - k, kc = min(k + 1, p.w_in - 1) - k;
+                    const T* q0 = row0 + k;
+                    const float w1a = cl1[0], w1b = cl1[1], w1c = cl1[2], w1d = cl1[3];
+                    const float w0a = 1.f - w1a, w0b = 1.f - w1b, w0c = 1.f - w1c, w0d = 1.f - w1d;
+#pragma unroll
+                    for (int c = 0; c < CMAX; ++c) {
+                        if (EXACT || c < C) {
+                            const float a0 = load_lowres<T>(q0 + ka), b0 = load_lowres<T>(q0), c0 = load_lowres<T>(q0 + kc);
+                            const float a1 = load_lowres<T>(q0 + down + ka), b1 = load_lowres<T>(q0 + down), c1 = load_lowres<T>(q0 + down + kc);
+                            v[c][0] = l0y * (w0a * a0 + w1a * b0) + l1y * (w0a * a1 + w1a * b1);
+                            v[c][1 % VEC] = l0y * (w0b * a0 + w1b * b0) + l1y * (w0b * a1 + w1b * b1);
+                            v[c][2 % VEC] = l0y * (w0c * b0 + w1c * c0) + l1y * (w0c * b1 + w1c * c1);
+                            v[c][3 % VEC] = l0y * (w0d * b0 + w1d * c0) + l1y * (w0d * b1 + w1d * c1);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < VEC; ++j) v[c][j] = -INFINITY;
+                        }
+                        q0 += P_src;
+                    }
+                } else {
 #pragma unroll
                 for (int c = 0; c < CMAX; ++c) {
                     if (EXACT || c < C) {
@@ -142,6 +172,7 @@ __global__ void __launch_bounds__(kAbreast * 32) bvsb_stats_abreast_kernel(const
                         for (int j = 0; j < VEC; ++j) v[c][j] = -INFINITY;
                     }
                     row0 += P_src;
+                }
                 }
             } else {
 #pragma unroll
@@ -176,7 +207,7 @@ __global__ void __launch_bounds__(kAbreast * 32) bvsb_stats_abreast_kernel(const
                 w.img_region += p.S;
             }
             if (at.img < p.n_img) {
-                for (int k = 1; k <= kAhead; ++k) prefetch_row(at.y + k);
+                for (int k = 1; k <= ahead; ++k) prefetch_row(at.y + k);
             }
         }
     }
@@ -206,6 +237,8 @@ cudaError_t launch_one(StatsParams p, cudaStream_t stream) {
     }
     const int strips = (p.W + 32 * VEC - 1) / (32 * VEC);
     p.strips = (strips + kAbreast - 1) / kAbreast;          // strip GROUPS per image
+    const char* ahead = getenv("MAS_SCORER_AHEAD");          // development switch
+    p.stages = (ahead && *ahead) ? std::min(std::max(atoi(ahead), 0), 8) : kAheadDefault;
     p.total_rows = (long long)p.n_img * p.strips * p.H;     // work units
     const long long cap = (p.total_rows + 7) / 8;           // never fewer than ~8 units per CTA
     const long long blocks = std::max<long long>(1, std::min<long long>((long long)mas::sm_count() * per_sm, cap));

@@ -431,12 +431,16 @@ def candidate_argmax(logits: torch.Tensor, spx: torch.Tensor, mask: torch.Tensor
 
 
 _workspaces = {}
+_workspace_bytes = {}
 
 
 def _labeller_workspace(device, fch, c, h, w, nseg) -> torch.Tensor:
     """Scratch of the prototype labeller, cached per (device, stream): calls on different streams never share (or
     regrow) a buffer that kernels queued on another stream still use."""
-    need = int(_lib.load().mas_proto_labeller_workspace_bytes(fch, c, h, w, nseg))
+    shape = (fch, c, h, w, nseg)
+    need = _workspace_bytes.get(shape)
+    if need is None:
+        need = _workspace_bytes[shape] = int(_lib.load().mas_proto_labeller_workspace_bytes(fch, c, h, w, nseg))
     index = device.index if device.index is not None else torch.cuda.current_device()
     key = (index, torch._C._cuda_getCurrentRawStream(index))
     buf = _workspaces.get(key)

@@ -133,6 +133,10 @@ def main():
         low_res(res, 19, torch.float32)
         return
     full_res(res, "voc_crop 513x513x22", 22, 513, 513, 150, 512, ["ldg", "default"])
+    for ahead in ("0", "1", "4"):
+        os.environ["MAS_SCORER_AHEAD"] = ahead
+        full_res(res, f"voc_crop 513x513x22 ahead={ahead}", 22, 513, 513, 150, 512, ["default"])
+    os.environ.pop("MAS_SCORER_AHEAD", None)
     full_res(res, "voc_native 375x500x22", 22, 375, 500, 150, 512, ["default", "abreast", "ldg"])
     full_res(res, "cityscapes 1024x2048x19", 19, 1024, 2048, 2048, 48, ["default", "abreast"])
     full_res(res, "cityscapes bf16 1024x2048x19", 19, 1024, 2048, 2048, 48, ["default", "abreast"], torch.bfloat16)
