@@ -298,6 +298,26 @@ int mas_multihot_loss_bwd_dev(const float* logits, const void* ids, int ids_dtyp
                               const uint64_t* group_max, const float* coef, int n_img, int channels, int height, int width,
                               int nseg, float temperature, int flags, float* grad_logits, void* stream);
 
+/* ACTIVE-TILE LIST of a mask.  In training only the labelled superpixels are selected (spmasks, 2-10 % of the pixels
+ * after a few acquisition rounds; trainer/active_joint_multi_predignore_lossdecomp.py:101-104 hands the same masks to both
+ * criteria).  mas_multihot_tiles_dev scans the mask once (tiles of 32 px x 8 rows) and writes a bitmap of the tiles that
+ * hold a selected pixel plus prefix sums into `tiles` (mas_multihot_tiles_workspace_bytes() bytes, 16-byte aligned).  The
+ * *_tiles_dev twins of the two passes take that list:
+ *   forward : only the active tiles are visited, dealt round-robin BY RANK to the warps (balanced whatever the layout of
+ *             the labelled regions; deterministic -- no atomic queue);
+ *   backward: when fewer than 35 % of the tiles are active the dense gradient is zeroed by one linear sweep and only the
+ *             active tiles are computed on top; otherwise the tile walk of mas_multihot_loss_bwd_dev runs unchanged.
+ * Results are those of the plain entry points (tiles == NULL falls back to them).
+ */
+size_t mas_multihot_tiles_workspace_bytes(int n_img, int height, int width);
+int mas_multihot_tiles_dev(const uint8_t* mask, int n_img, int height, int width, void* tiles, size_t tiles_bytes, void* stream);
+int mas_multihot_loss_fwd_tiles_dev(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask, const uint32_t* info,
+                                    const void* tiles, int n_img, int channels, int height, int width, int nseg, float temperature,
+                                    int flags, double* acc, uint64_t* group_max, void* stream);
+int mas_multihot_loss_bwd_tiles_dev(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask, const uint32_t* info,
+                                    const void* tiles, const uint64_t* group_max, const float* coef, int n_img, int channels,
+                                    int height, int width, int nseg, float temperature, int flags, float* grad_logits, void* stream);
+
 /* mas_multihot_loss_finish_dev -- the reference's normalisations (counters start at 1; fp32 sum / fp32 count, like
  * `loss / num_valid`) of the bucket sums in `acc`, in one launch.  losses = 6 DEVICE floats:
  *   [0] one-hot CE                  acc[0] / (1 + acc[1])                      ..._predignore_lossdecomp.py:69, ..._lossdecomp.py:71

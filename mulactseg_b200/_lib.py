@@ -56,6 +56,12 @@ SIGNATURES = {
     "mas_multihot_info_dev": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mas_multihot_loss_fwd_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                           c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "mas_multihot_tiles_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "mas_multihot_tiles_dev": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "mas_multihot_loss_fwd_tiles_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                                c_int, c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "mas_multihot_loss_bwd_tiles_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                                c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     "mas_multihot_loss_finish_dev": (c_int, [c_void_p, c_void_p, c_void_p]),
     "mas_multihot_loss_coef_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "mas_candidate_argmax_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -16,7 +16,7 @@ void set_error(const char* fmt, ...);
 // losses.cu: the fused loss forward pass; `reduce_group` = false skips the group-loss reduction launch (stage-2 labeller)
 int multihot_loss_fwd(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask, const uint32_t* info, int n_img,
                       int channels, int height, int width, int nseg, float temperature, int flags, double* acc,
-                      uint64_t* group_max, bool reduce_group, void* stream);
+                      uint64_t* group_max, bool reduce_group, void* stream, const void* tiles = nullptr);
 void count_launches(int n);  // bookkeeping for mas_kernel_launches()
 
 inline int cuda_fail(cudaError_t e, const char* what) {

@@ -756,7 +756,7 @@ int proto_labeller_impl(const char* what, const void* feats, int feat_dtype, int
     // arg-max-probability pixel per (superpixel, candidate class): softmax with T = 1 (:140); the group loss itself is not needed
     int rc = mas::multihot_loss_fwd(logits, ids, ids_dtype, mask, w.info, 1, channels, height, width, nseg, 1.0f,
                                     MAS_LOSS_CHOICE | MAS_LOSS_GROUP | MAS_LOSS_EXACT_SOFTMAX, w.acc, reinterpret_cast<uint64_t*>(w.gmax),
-                                    false, stream);
+                                    false, stream, nullptr);
     if (rc != 0) return rc;
 
     LabelParams p = {};

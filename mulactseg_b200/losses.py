@@ -41,10 +41,10 @@ class _SegmentedLossSums(torch.autograd.Function):
     counts (4,) f64 (not differentiable)."""
 
     @staticmethod
-    def forward(ctx, inputs, spx, mask, info, nseg, temperature, flags):
+    def forward(ctx, inputs, spx, mask, info, tiles, nseg, temperature, flags):
         x = inputs.contiguous()
-        acc, gmax = ops.multihot_loss_forward(x, spx, mask, info, nseg, temperature, flags)
-        ctx.save_for_backward(x, spx, mask, info, gmax if gmax is not None else torch.empty(0, device=x.device))
+        acc, gmax = ops.multihot_loss_forward(x, spx, mask, info, nseg, temperature, flags, tiles)
+        ctx.save_for_backward(x, spx, mask, info, tiles, gmax if gmax is not None else torch.empty(0, device=x.device))
         ctx.nseg, ctx.temperature, ctx.flags = nseg, temperature, flags
         sums = acc[0::2].to(torch.float32)
         counts = acc[1::2].clone()
@@ -53,11 +53,11 @@ class _SegmentedLossSums(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_sums, _grad_counts):
-        x, spx, mask, info, gmax = ctx.saved_tensors
+        x, spx, mask, info, tiles, gmax = ctx.saved_tensors
         coef = grad_sums.to(torch.float32).contiguous()
         grad = ops.multihot_loss_backward(x, spx, mask, info, gmax if gmax.numel() else None, coef, ctx.nseg,
-                                          ctx.temperature, ctx.flags & ~_lib.MAS_LOSS_EXACT_SOFTMAX)
-        return grad, None, None, None, None, None, None
+                                          ctx.temperature, ctx.flags & ~_lib.MAS_LOSS_EXACT_SOFTMAX, tiles)
+        return grad, None, None, None, None, None, None, None
 
 
 class _SegmentedLosses(torch.autograd.Function):
@@ -67,11 +67,11 @@ class _SegmentedLosses(torch.autograd.Function):
     and 3 backward (stack of the incoming gradients, coefficients, fused pass)."""
 
     @staticmethod
-    def forward(ctx, inputs, spx, mask, info, nseg, temperature, flags):
+    def forward(ctx, inputs, spx, mask, info, tiles, nseg, temperature, flags):
         x = inputs.contiguous()
-        acc, gmax = ops.multihot_loss_forward(x, spx, mask, info, nseg, temperature, flags)
+        acc, gmax = ops.multihot_loss_forward(x, spx, mask, info, nseg, temperature, flags, tiles)
         losses = ops.multihot_loss_finish(acc)
-        ctx.save_for_backward(x, spx, mask, info, acc, gmax if gmax is not None else torch.empty(0, device=x.device))
+        ctx.save_for_backward(x, spx, mask, info, tiles, acc, gmax if gmax is not None else torch.empty(0, device=x.device))
         ctx.nseg, ctx.temperature, ctx.flags = nseg, temperature, flags
         ctx.set_materialize_grads(False)
         counts = acc[1::2]
@@ -80,10 +80,10 @@ class _SegmentedLosses(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        x, spx, mask, info, acc, gmax = ctx.saved_tensors
+        x, spx, mask, info, tiles, acc, gmax = ctx.saved_tensors
         grads = grads[:6]
         if all(g is None for g in grads):
-            return (None,) * 7
+            return (None,) * 8
         zero = None
         parts = []
         for g in grads:
@@ -94,8 +94,8 @@ class _SegmentedLosses(torch.autograd.Function):
             parts.append(g.to(torch.float32).reshape(()))
         coef = ops.multihot_loss_coef(acc, torch.stack(parts))
         grad = ops.multihot_loss_backward(x, spx, mask, info, gmax if gmax.numel() else None, coef, ctx.nseg,
-                                          ctx.temperature, ctx.flags & ~_lib.MAS_LOSS_EXACT_SOFTMAX)
-        return grad, None, None, None, None, None, None
+                                          ctx.temperature, ctx.flags & ~_lib.MAS_LOSS_EXACT_SOFTMAX, tiles)
+        return grad, None, None, None, None, None, None, None
 
 
 # positions in the tuple returned by ``segmented_losses``
@@ -124,7 +124,7 @@ def segmented_loss_sums(inputs, targets, superpixels, spmasks, temperature: floa
     flags = (_lib.MAS_LOSS_CHOICE if want_choice else 0) | (_lib.MAS_LOSS_GROUP if group_mode is not None else 0)
     if EXACT_SOFTMAX:
         flags |= _lib.MAS_LOSS_EXACT_SOFTMAX
-    return _SegmentedLossSums.apply(inputs, spx, mask, info, nseg, float(temperature), flags)
+    return _SegmentedLossSums.apply(inputs, spx, mask, info, ops.multihot_tiles(mask), nseg, float(temperature), flags)
 
 
 def segmented_losses(inputs, targets, superpixels, spmasks, temperature: float, group_mode: Optional[int], want_choice: bool):
@@ -136,7 +136,7 @@ def segmented_losses(inputs, targets, superpixels, spmasks, temperature: float, 
     flags = (_lib.MAS_LOSS_CHOICE if want_choice else 0) | (_lib.MAS_LOSS_GROUP if group_mode is not None else 0)
     if EXACT_SOFTMAX:
         flags |= _lib.MAS_LOSS_EXACT_SOFTMAX
-    return _SegmentedLosses.apply(inputs, spx, mask, info, nseg, float(temperature), flags)
+    return _SegmentedLosses.apply(inputs, spx, mask, info, ops.multihot_tiles(mask), nseg, float(temperature), flags)
 
 
 class SharedPass:

@@ -353,6 +353,24 @@ def multihot_info(targets: torch.Tensor, channels: int, group_mode: int) -> torc
     return info
 
 
+_tile_bytes = {}
+
+
+def multihot_tiles(mask: torch.Tensor) -> torch.Tensor:
+    """(N,H,W) bool|uint8 mask -> the active-tile list both loss passes take (``mas_multihot_tiles_dev``): which 32 px x 8 row
+    tiles hold a selected pixel, with prefix sums.  One scan of the mask; reused by the forward and the backward pass."""
+    _want(mask, "spmasks", (torch.bool, torch.uint8), 3)
+    n, h, w = mask.shape
+    need = _tile_bytes.get((n, h, w))
+    if need is None:
+        need = _tile_bytes[(n, h, w)] = int(_lib.load().mas_multihot_tiles_workspace_bytes(n, h, w))
+    tiles = torch.empty(need, dtype=torch.uint8, device=mask.device)
+    if n * h * w:
+        with _on(mask):
+            _lib.call("mas_multihot_tiles_dev", mask.data_ptr(), n, h, w, tiles.data_ptr(), need, _stream(mask))
+    return tiles
+
+
 def _loss_args(logits, spx, mask, info, nseg):
     _want(logits, "inputs", torch.float32, 4)
     _want(spx, "superpixels", (torch.int32, torch.int64), 3)
@@ -367,8 +385,9 @@ def _loss_args(logits, spx, mask, info, nseg):
 
 
 def multihot_loss_forward(logits: torch.Tensor, spx: torch.Tensor, mask: torch.Tensor, info: torch.Tensor, nseg: int,
-                          temperature: float, flags: int):
-    """-> (acc (8,) f64 bucket sums / counts, group_max (N,nseg,C) i64 packed maxima or None)."""
+                          temperature: float, flags: int, tiles: Optional[torch.Tensor] = None):
+    """-> (acc (8,) f64 bucket sums / counts, group_max (N,nseg,C) i64 packed maxima or None).
+    ``tiles``: the active-tile list of ``mask`` (``multihot_tiles``) -- only tiles with selected pixels are visited."""
     n, c, h, w = _loss_args(logits, spx, mask, info, nseg)
     # one zero-fill for both: 8 accumulators (viewed as f64) followed by the max-pool table
     want_group = bool(flags & _lib.MAS_LOSS_GROUP)
@@ -376,24 +395,25 @@ def multihot_loss_forward(logits: torch.Tensor, spx: torch.Tensor, mask: torch.T
     acc = buf[:8].view(torch.float64)
     gmax = buf[8:].view(n, nseg, c) if want_group else None
     with _on(logits):
-        _lib.call("mas_multihot_loss_fwd_dev", logits.data_ptr(), spx.data_ptr(), _ids_dtype(spx), mask.data_ptr(),
-                  info.data_ptr(), n, c, h, w, int(nseg), float(temperature), int(flags), acc.data_ptr(), _ptr(gmax),
+        _lib.call("mas_multihot_loss_fwd_tiles_dev", logits.data_ptr(), spx.data_ptr(), _ids_dtype(spx), mask.data_ptr(),
+                  info.data_ptr(), _ptr(tiles), n, c, h, w, int(nseg), float(temperature), int(flags), acc.data_ptr(), _ptr(gmax),
                   _stream(logits))
     return acc, gmax
 
 
 def multihot_loss_backward(logits: torch.Tensor, spx: torch.Tensor, mask: torch.Tensor, info: torch.Tensor,
                            gmax: Optional[torch.Tensor], coef: torch.Tensor, nseg: int, temperature: float,
-                           flags: int) -> torch.Tensor:
-    """Dense d(sum_k coef[k] * bucket_sum[k]) / d logits; coef = 4 device floats."""
+                           flags: int, tiles: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Dense d(sum_k coef[k] * bucket_sum[k]) / d logits; coef = 4 device floats.  ``tiles`` as in the forward pass: a
+    sparsely selected batch gets its gradient zeroed by one linear sweep and only the active tiles computed."""
     n, c, h, w = _loss_args(logits, spx, mask, info, nseg)
     _want(coef, "coef", torch.float32, 1)
     if coef.numel() != 4:
         raise RuntimeError("coef must hold 4 floats")
     grad = torch.empty_like(logits)
     with _on(logits):
-        _lib.call("mas_multihot_loss_bwd_dev", logits.data_ptr(), spx.data_ptr(), _ids_dtype(spx), mask.data_ptr(),
-                  info.data_ptr(), _ptr(gmax), coef.data_ptr(), n, c, h, w, int(nseg), float(temperature), int(flags),
+        _lib.call("mas_multihot_loss_bwd_tiles_dev", logits.data_ptr(), spx.data_ptr(), _ids_dtype(spx), mask.data_ptr(),
+                  info.data_ptr(), _ptr(tiles), _ptr(gmax), coef.data_ptr(), n, c, h, w, int(nseg), float(temperature), int(flags),
                   grad.data_ptr(), _stream(logits))
     return grad
 

@@ -140,7 +140,8 @@ def test_shared_pass_equals_separate_passes_and_trainer_total():
     loss.backward()
     torch.cuda.synchronize()
     launches = _lib.load().mas_kernel_launches() - before
-    assert launches == 6        # info + fused forward + group reduce + finish; coefficients + fused backward
+    # candidate words + active-tile scan + fused forward + group reduce + finish; coefficients + zero sweep + fused backward
+    assert launches == 8
     np.testing.assert_allclose([ce.item(), mc.item(), g.item()], [ce_ref.item(), mc_ref.item(), group_ref.item()], rtol=RTOL)
     np.testing.assert_allclose(loss.item(), total_ref.item(), rtol=RTOL)
     ref_grad = xr.grad.numpy()
