@@ -332,6 +332,24 @@ int mas_multihot_loss_bwd_tiles_dev(const float* logits, const void* ids, int id
 int mas_multihot_loss_finish_dev(const double* acc, float* losses, void* stream);
 int mas_multihot_loss_coef_dev(const double* acc, const float* grad_losses, float* coef, void* stream);
 
+/* mas_stage1_loss_fwd_dev / mas_stage1_loss_bwd_dev -- the trainer's whole loss step
+ * (trainer/active_joint_multi_predignore_lossdecomp.py:101-107: group loss + decomposed partial-label loss on the same
+ * tensors) in ONE call per direction: candidate words (mas_multihot_info_dev), active-tile list, fused forward, group
+ * reduction and the six normalised losses of mas_multihot_loss_finish_dev; then coefficients, zero sweep and the fused
+ * backward.  Same launches as the separate entry points, an eighth of the host work (at a few percent of labelled pixels
+ * the host side of the step, not its kernels, is the bottleneck).  `workspace`: mas_stage1_workspace_bytes() bytes,
+ * 16-byte aligned, kept by the caller from forward to backward; bytes [0,64) = acc (8 doubles), [64,88) = the six losses.
+ * targets (n_img, nseg, target_channels) uint8, group_mode as mas_multihot_info_dev, flags as mas_multihot_loss_fwd_dev.
+ * grad_losses: HOST array of six DEVICE pointers to the incoming gradients of the six losses (NULL = not used).
+ */
+size_t mas_stage1_workspace_bytes(int n_img, int channels, int height, int width, int nseg);
+int mas_stage1_loss_fwd_dev(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask, const uint8_t* targets,
+                            int target_channels, int n_img, int channels, int height, int width, int nseg, float temperature,
+                            int group_mode, int flags, void* workspace, size_t workspace_bytes, void* stream);
+int mas_stage1_loss_bwd_dev(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask, int n_img, int channels,
+                            int height, int width, int nseg, float temperature, int flags, const void* workspace,
+                            const float* const* grad_losses, float* grad_logits, void* stream);
+
 /* ------------------------------------------------------------------ stage-2 pseudo-labellers
  *
  * mas_candidate_argmax_dev -- trainer/eval_within_multihot.py:93-146 top_pseudo_label_generation:

@@ -62,6 +62,11 @@ SIGNATURES = {
                                                 c_int, c_float, c_int, c_void_p, c_void_p, c_void_p]),
     "mas_multihot_loss_bwd_tiles_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                                 c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "mas_stage1_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "mas_stage1_loss_fwd_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "mas_stage1_loss_bwd_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "mas_multihot_loss_finish_dev": (c_int, [c_void_p, c_void_p, c_void_p]),
     "mas_multihot_loss_coef_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "mas_candidate_argmax_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

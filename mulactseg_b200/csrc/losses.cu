@@ -905,3 +905,96 @@ extern "C" int mas_multihot_loss_coef_dev(const double* acc, const float* grad_l
     MAS_LAUNCH_OK("loss_coef_kernel");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------ whole loss step in two calls
+// The trainer's step (trainer/active_joint_multi_predignore_lossdecomp.py:101-107) through the entry points above is five
+// host calls forward and three backward plus their temporaries -- at a few percent of labelled pixels that host work
+// (0.4 ms in Python) exceeds the 0.25 ms the kernels need.  These two entries run the same launches from ONE call each,
+// on one caller-provided workspace:
+//   [0, 64)    acc      8 doubles (bucket sums / counts)          [64, 96)  losses  6 floats (+ pad)
+//   [96, 128)  coef     4 floats (backward)                       then: candidate words, active-tile list, packed maxima
+namespace {
+
+struct StepSpace {
+    double* acc; float* losses; float* coef; uint32_t* info; void* tiles; uint64_t* gmax; size_t tiles_bytes, zero_from, bytes;
+};
+
+size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+StepSpace carve_step(void* base, int n_img, int channels, int height, int width, int nseg) {
+    char* b = reinterpret_cast<char*>(base);
+    StepSpace w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* q = b ? b + off : nullptr; off += up16(bytes); return q; };
+    w.acc = reinterpret_cast<double*>(take(64));
+    w.losses = reinterpret_cast<float*>(take(32));
+    w.coef = reinterpret_cast<float*>(take(32));
+    w.info = reinterpret_cast<uint32_t*>(take((size_t)n_img * nseg * 4));
+    w.tiles_bytes = mas_multihot_tiles_workspace_bytes(n_img, height, width);
+    w.tiles = take(w.tiles_bytes);
+    w.zero_from = off;
+    w.gmax = reinterpret_cast<uint64_t*>(take((size_t)n_img * nseg * channels * 8));
+    w.bytes = off;
+    return w;
+}
+
+// coef[k] = d (sum_j grad_j * losses[j]) / d (bucket sum k) with the incoming gradients given as six device pointers
+// (NULL = that loss does not take part)
+struct GradPtrs { const float* g[6]; };
+
+__global__ void loss_coef_ptr_kernel(const double* __restrict__ acc, GradPtrs grads, float* __restrict__ coef) {
+    if (threadIdx.x != 0) return;
+    float g[6];
+    for (int j = 0; j < 6; ++j) g[j] = grads.g[j] ? *grads.g[j] : 0.f;
+    const double n0 = acc[1], n1 = acc[3], n2 = acc[5], n3 = acc[7];
+    const float d0 = (float)(1.0 + n0), d1 = (float)(1.0 + n1), d12 = (float)(1.0 + n1 + n2), d01 = (float)(1.0 + n0 + n1);
+    coef[0] = g[0] / d0 + g[3] / d01;
+    coef[1] = g[1] / d1 + g[2] / d12 + g[3] / d01;
+    coef[2] = g[2] / d12;
+    coef[3] = g[4] / (float)(1.0 + n3);
+}
+
+}  // namespace
+
+extern "C" size_t mas_stage1_workspace_bytes(int n_img, int channels, int height, int width, int nseg) {
+    if (n_img <= 0 || channels <= 0 || height <= 0 || width <= 0 || nseg <= 0) return 0;
+    return carve_step(nullptr, n_img, channels, height, width, nseg).bytes;
+}
+
+extern "C" int mas_stage1_loss_fwd_dev(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask, const uint8_t* targets,
+                                       int target_channels, int n_img, int channels, int height, int width, int nseg,
+                                       float temperature, int group_mode, int flags, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+    MAS_REQUIRE(logits && ids && mask && targets && workspace, MAS_E_BADARG, "stage1_loss_fwd: null pointer");
+    MAS_REQUIRE(n_img > 0 && height > 0 && width > 0 && nseg > 0, MAS_E_BADARG, "stage1_loss_fwd: bad shape");
+    MAS_REQUIRE(((uintptr_t)workspace) % 16 == 0, MAS_E_BADARG, "stage1_loss_fwd: workspace must be 16-byte aligned");
+    const StepSpace w = carve_step(workspace, n_img, channels, height, width, nseg);
+    MAS_REQUIRE(workspace_bytes >= w.bytes, MAS_E_WORKSPACE, "stage1_loss_fwd: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    MAS_CUDA_OK(cudaMemsetAsync(workspace, 0, 128, st));                                            // acc, losses, coef
+    if (flags & MAS_LOSS_GROUP) MAS_CUDA_OK(cudaMemsetAsync(w.gmax, 0, w.bytes - w.zero_from, st));
+    int rc = mas_multihot_info_dev(targets, (int64_t)n_img * nseg, target_channels, channels, group_mode, w.info, stream);
+    if (rc != 0) return rc;
+    rc = mas_multihot_tiles_dev(mask, n_img, height, width, w.tiles, w.tiles_bytes, stream);
+    if (rc != 0) return rc;
+    rc = mas::multihot_loss_fwd(logits, ids, ids_dtype, mask, w.info, n_img, channels, height, width, nseg, temperature, flags, w.acc,
+                                (flags & MAS_LOSS_GROUP) ? w.gmax : nullptr, true, stream, w.tiles);
+    if (rc != 0) return rc;
+    return mas_multihot_loss_finish_dev(w.acc, w.losses, stream);
+}
+
+extern "C" int mas_stage1_loss_bwd_dev(const float* logits, const void* ids, int ids_dtype, const uint8_t* mask, int n_img, int channels,
+                                       int height, int width, int nseg, float temperature, int flags, const void* workspace,
+                                       const float* const* grad_losses, float* grad_logits, void* stream) {
+    MAS_REQUIRE(logits && ids && mask && workspace && grad_losses && grad_logits, MAS_E_BADARG, "stage1_loss_bwd: null pointer");
+    MAS_REQUIRE(n_img > 0 && height > 0 && width > 0 && nseg > 0, MAS_E_BADARG, "stage1_loss_bwd: bad shape");
+    const StepSpace w = carve_step(const_cast<void*>(workspace), n_img, channels, height, width, nseg);
+    GradPtrs grads;
+    for (int j = 0; j < 6; ++j) grads.g[j] = grad_losses[j];
+    loss_coef_ptr_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(w.acc, grads, w.coef);
+    mas::count_launches(1);
+    MAS_LAUNCH_OK("loss_coef_ptr_kernel");
+    return mas_multihot_loss_bwd_tiles_dev(logits, ids, ids_dtype, mask, w.info, w.tiles, (flags & MAS_LOSS_GROUP) ? w.gmax : nullptr, w.coef,
+                                           n_img, channels, height, width, nseg, temperature, flags & ~MAS_LOSS_EXACT_SOFTMAX, grad_logits,
+                                           stream);
+}

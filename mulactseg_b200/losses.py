@@ -63,15 +63,15 @@ class _SegmentedLossSums(torch.autograd.Function):
 class _SegmentedLosses(torch.autograd.Function):
     """The same fused pass as ``_SegmentedLossSums`` with the reference's normalisations folded in on the device:
     returns the six 0-dim losses of ``mas_multihot_loss_finish_dev`` (views of one (6,) tensor) and the bucket
-    counts (4,) f64.  A step is 5 launches forward (zero-fill, candidate words, fused pass, group reduce, finish)
-    and 3 backward (stack of the incoming gradients, coefficients, fused pass)."""
+    counts (4,) f64.  The whole forward side is ONE library call on one workspace (``mas_stage1_loss_fwd_dev``: candidate
+    words, active-tile list, fused pass, group reduce, finish) and so is the backward side (coefficients, zero sweep,
+    fused pass): at a few percent of labelled pixels the host work of a step, not its kernels, sets the pace."""
 
     @staticmethod
-    def forward(ctx, inputs, spx, mask, info, tiles, nseg, temperature, flags):
+    def forward(ctx, inputs, trg, spx, mask, nseg, temperature, group_mode, flags):
         x = inputs.contiguous()
-        acc, gmax = ops.multihot_loss_forward(x, spx, mask, info, nseg, temperature, flags, tiles)
-        losses = ops.multihot_loss_finish(acc)
-        ctx.save_for_backward(x, spx, mask, info, tiles, acc, gmax if gmax is not None else torch.empty(0, device=x.device))
+        ws, acc, losses = ops.stage1_forward(x, spx, mask, trg, temperature, group_mode, flags)
+        ctx.save_for_backward(x, spx, mask, ws)
         ctx.nseg, ctx.temperature, ctx.flags = nseg, temperature, flags
         ctx.set_materialize_grads(False)
         counts = acc[1::2]
@@ -80,21 +80,11 @@ class _SegmentedLosses(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        x, spx, mask, info, tiles, acc, gmax = ctx.saved_tensors
+        x, spx, mask, ws = ctx.saved_tensors
         grads = grads[:6]
         if all(g is None for g in grads):
             return (None,) * 8
-        zero = None
-        parts = []
-        for g in grads:
-            if g is None:
-                if zero is None:
-                    zero = torch.zeros((), dtype=torch.float32, device=x.device)
-                g = zero
-            parts.append(g.to(torch.float32).reshape(()))
-        coef = ops.multihot_loss_coef(acc, torch.stack(parts))
-        grad = ops.multihot_loss_backward(x, spx, mask, info, gmax if gmax.numel() else None, coef, ctx.nseg,
-                                          ctx.temperature, ctx.flags & ~_lib.MAS_LOSS_EXACT_SOFTMAX, tiles)
+        grad = ops.stage1_backward(x, spx, mask, ws, ctx.nseg, ctx.temperature, ctx.flags, grads)
         return grad, None, None, None, None, None, None, None
 
 
@@ -131,12 +121,13 @@ def segmented_losses(inputs, targets, superpixels, spmasks, temperature: float, 
     """Like ``segmented_loss_sums`` but normalised on the device: -> tuple indexed by ONE_HOT .. GROUP (0-dim losses)
     and COUNTS ((4,) f64 bucket counts)."""
     trg, spx, mask = _prepare(inputs, targets, superpixels, spmasks)
-    nseg = trg.shape[1]
-    info = ops.multihot_info(trg, inputs.shape[1], _lib.MAS_GROUP_ALL if group_mode is None else group_mode)
+    if trg.shape[2] < inputs.shape[1]:
+        raise RuntimeError(f"targets carry {trg.shape[2]} channels, fewer than the {inputs.shape[1]} logit channels")
     flags = (_lib.MAS_LOSS_CHOICE if want_choice else 0) | (_lib.MAS_LOSS_GROUP if group_mode is not None else 0)
     if EXACT_SOFTMAX:
         flags |= _lib.MAS_LOSS_EXACT_SOFTMAX
-    return _SegmentedLosses.apply(inputs, spx, mask, info, ops.multihot_tiles(mask), nseg, float(temperature), flags)
+    return _SegmentedLosses.apply(inputs, trg, spx, mask, trg.shape[1], float(temperature),
+                                  _lib.MAS_GROUP_ALL if group_mode is None else group_mode, flags)
 
 
 class SharedPass:

@@ -418,6 +418,48 @@ def multihot_loss_backward(logits: torch.Tensor, spx: torch.Tensor, mask: torch.
     return grad
 
 
+_step_bytes = {}
+
+
+def stage1_forward(logits: torch.Tensor, spx: torch.Tensor, mask: torch.Tensor, targets: torch.Tensor, temperature: float,
+                   group_mode: int, flags: int):
+    """The whole forward side of the loss step in ONE library call (``mas_stage1_loss_fwd_dev``): candidate words,
+    active-tile list, fused pass, group reduction, normalised losses.
+    -> (workspace (opaque, needed by ``stage1_backward``), acc (8,) f64 view, losses (6,) f32 view)."""
+    _want(logits, "inputs", torch.float32, 4)
+    _want(spx, "superpixels", (torch.int32, torch.int64), 3)
+    _want(mask, "spmasks", (torch.bool, torch.uint8), 3)
+    _want(targets, "targets", torch.uint8, 3)
+    n, c, h, w = logits.shape
+    nseg, ct = targets.shape[1], targets.shape[2]
+    if tuple(spx.shape) != (n, h, w) or tuple(mask.shape) != (n, h, w) or targets.shape[0] != n:
+        raise RuntimeError(f"superpixels {tuple(spx.shape)} / spmasks {tuple(mask.shape)} / targets {tuple(targets.shape)} "
+                           f"do not match inputs {tuple(logits.shape)}")
+    key = (n, c, h, w, nseg)
+    need = _step_bytes.get(key)
+    if need is None:
+        need = _step_bytes[key] = int(_lib.load().mas_stage1_workspace_bytes(n, c, h, w, nseg))
+    ws = torch.empty(need, dtype=torch.uint8, device=logits.device)
+    with _on(logits):
+        _lib.call("mas_stage1_loss_fwd_dev", logits.data_ptr(), spx.data_ptr(), _ids_dtype(spx), mask.data_ptr(), targets.data_ptr(), ct,
+                  n, c, h, w, nseg, float(temperature), int(group_mode), int(flags), ws.data_ptr(), need, _stream(logits))
+    return ws, ws[:64].view(torch.float64), ws[64:88].view(torch.float32)
+
+
+def stage1_backward(logits: torch.Tensor, spx: torch.Tensor, mask: torch.Tensor, ws: torch.Tensor, nseg: int, temperature: float,
+                    flags: int, grads) -> torch.Tensor:
+    """Dense gradient of sum_j grads[j] * losses[j] (``mas_stage1_loss_bwd_dev``); ``grads``: six 0-dim fp32 CUDA tensors or None."""
+    import ctypes
+    n, c, h, w = logits.shape
+    keep = [None if g is None else (g if g.dtype == torch.float32 else g.float()) for g in grads]
+    ptrs = (ctypes.c_void_p * 6)(*[None if g is None else g.data_ptr() for g in keep])
+    grad = torch.empty_like(logits)
+    with _on(logits):
+        _lib.call("mas_stage1_loss_bwd_dev", logits.data_ptr(), spx.data_ptr(), _ids_dtype(spx), mask.data_ptr(), n, c, h, w, int(nseg),
+                  float(temperature), int(flags), ws.data_ptr(), ptrs, grad.data_ptr(), _stream(logits))
+    return grad
+
+
 def multihot_loss_finish(acc: torch.Tensor) -> torch.Tensor:
     """(8,) f64 bucket sums / counts -> (6,) f32 normalised losses (see ``mas_multihot_loss_finish_dev``)."""
     _want(acc, "acc", torch.float64, 1)
