@@ -350,6 +350,26 @@ int mas_stage1_loss_bwd_dev(const float* logits, const void* ids, int ids_dtype,
                             int height, int width, int nseg, float temperature, int flags, const void* workspace,
                             const float* const* grad_losses, float* grad_logits, void* stream);
 
+/* ------------------------------------------------------------------ operator level: torch_scatter
+ *
+ * The reference delegates every segmented reduction to torch_scatter 2.0.9 (actsegmul.yml:99; call sites: SURVEY.md 2b).
+ * The twelve hot-path plugins never materialise those operands (fused passes above); these two entries serve the
+ * reference's OTHER call sites through mulactseg_b200/torch_scatter_compat.py (`scatter`, `scatter_max`, same
+ * signatures).  `src` is viewed as (outer, n, inner) with the reduced dimension in the middle; index is int64, either of
+ * src's shape (index_has_inner = 1) or (outer, n) shared by the `inner` trailing elements (the broadcast torch_scatter
+ * applies to e.g. a (B, HW) index against a (B, HW, C') one-hot, my_bvsb_banignore.py:44-45).  Indices outside
+ * [0, dim_size) are ignored.
+ *   mas_scatter_sum_dev: out (outer, dim_size, inner) += src   (float32 or int64; ACCUMULATES: zero `out` first).
+ *   mas_scatter_max_dev: out = per-segment maximum, 0 for a segment nobody writes; arg = FIRST position along the reduced
+ *     dimension attaining it (torch_scatter's CPU tie rule), pre-filled by the caller with n (the "empty" marker,
+ *     utils/loss.py:202-204).  key_workspace: outer * dim_size * inner uint32.
+ */
+#define MAS_SCATTER_I64 3
+int mas_scatter_sum_dev(const void* src, int src_dtype, const int64_t* index, int64_t outer, int64_t n, int64_t inner,
+                        int index_has_inner, int64_t dim_size, void* out, void* stream);
+int mas_scatter_max_dev(const float* src, const int64_t* index, int64_t outer, int64_t n, int64_t inner, int index_has_inner,
+                        int64_t dim_size, float* out, int64_t* arg, uint32_t* key_workspace, void* stream);
+
 /* ------------------------------------------------------------------ stage-2 pseudo-labellers
  *
  * mas_candidate_argmax_dev -- trainer/eval_within_multihot.py:93-146 top_pseudo_label_generation:

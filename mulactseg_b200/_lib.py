@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmulactseg_b200.so")
 
 MAS_F32, MAS_BF16 = 0, 1
 MAS_I32, MAS_I64, MAS_U8 = 0, 1, 2
+MAS_SCATTER_I64 = 3
 MAS_MIOU_BY_TARGET, MAS_MIOU_BY_OUTPUT = 0, 1
 MAS_GROUP_ALL, MAS_GROUP_ONLYMULTI = 0, 1
 MAS_LOSS_CHOICE, MAS_LOSS_GROUP, MAS_LOSS_EXACT_SOFTMAX = 1, 2, 4
@@ -53,6 +54,8 @@ SIGNATURES = {
     "mas_acquisition_host": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_float,
                                      c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mas_select_topk_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p]),
+    "mas_scatter_sum_dev": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int, c_int64, c_void_p, c_void_p]),
+    "mas_scatter_max_dev": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mas_multihot_info_dev": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mas_multihot_loss_fwd_dev": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                           c_float, c_int, c_void_p, c_void_p, c_void_p]),

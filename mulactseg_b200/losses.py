@@ -235,9 +235,12 @@ class MultiChoiceCE(_SegmentedLoss):
         self.num_class = num_class
 
     def forward(self, inputs, targets, superpixels, spmasks):
-        if self.reduction != "mean":
-            raise NotImplementedError("only reduction='mean' (what the shipped recipes use) is provided")
-        return self._losses(inputs, targets, superpixels, spmasks)[CHOICE_ALL]
+        if self.reduction == "mean":
+            return self._losses(inputs, targets, superpixels, spmasks)[CHOICE_ALL]
+        if self.reduction == "none":                     # (loss sum, num_valid), utils/loss.py:583-586; empty rows dropped (:574-577)
+            sums, counts = segmented_loss_sums(inputs, targets, superpixels, spmasks, self.temp, None, True)
+            return sums[0] + sums[1], 1 + counts[0] + counts[1]
+        raise NotImplementedError
 
 
 class MultiChoiceCE_(MultiChoiceCE):

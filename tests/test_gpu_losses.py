@@ -156,6 +156,26 @@ def test_shared_pass_equals_separate_passes_and_trainer_total():
     assert g2.item() == alone.item() and ce2.item() == ce.item() and mc2.item() == mc.item()
 
 
+def test_reduction_none_returns_sum_and_count_like_the_reference():
+    """utils/loss.py:137-139 and :583-586: reduction='none' hands back (loss sum, num_valid) for the caller to combine."""
+    from mulactseg_b200 import losses as L
+    n, c, h, w, nseg = 2, 9, 24, 40, 12
+    x = synth.logits(n, c, h, w, "cosine", seed=1)
+    spx = synth.pad_border(synth.superpixel_map(n, h, w, nseg, "jitter", seed=2), nseg, 2)
+    trg = synth.multihot_targets(n, nseg, c + 1, seed=3, p_extra=0.2)
+    mask = synth.region_mask(spx, nseg, 0.7, seed=4)
+    args = types.SimpleNamespace()
+    xd, td, sd, md = x.to(DEV), trg.to(DEV), spx.to(DEV), mask.to(DEV)
+    for make, oracle in ((lambda red: L.MultiChoiceCE(c, temperature=0.1, reduction=red),
+                          lambda: olo.multi_choice_ce(x, trg, spx, mask, 0.1, "base")),
+                         (lambda red: L.GroupMultiLabelCE(args, c, nseg, temperature=0.1, reduction=red),
+                          lambda: olo.group_multilabel_ce(x, trg, spx, mask, nseg, 0.1, "base"))):
+        total, count = make("none")(xd, td, sd, md)
+        mean = make("mean")(xd, td, sd, md)
+        np.testing.assert_allclose(float(total) / float(count), float(mean), rtol=1e-6)
+        np.testing.assert_allclose(float(mean), float(oracle()), rtol=RTOL)
+
+
 def test_shared_pass_never_serves_stale_results():
     from mulactseg_b200 import losses as L
     n, c, h, w, nseg = 2, 8, 16, 32, 8
