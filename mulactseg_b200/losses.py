@@ -109,6 +109,8 @@ def segmented_loss_sums(inputs, targets, superpixels, spmasks, temperature: floa
     """One fused pass.  ``group_mode``: None (no group loss), MAS_GROUP_ALL or MAS_GROUP_ONLYMULTI.
     The candidate sets are the first ``inputs.shape[1]`` target channels (== ``targets[..., :C']``)."""
     trg, spx, mask = _prepare(inputs, targets, superpixels, spmasks)
+    if inputs.dtype != torch.float32:
+        inputs = inputs.float()
     nseg = trg.shape[1]
     info = ops.multihot_info(trg, inputs.shape[1], _lib.MAS_GROUP_ALL if group_mode is None else group_mode)
     flags = (_lib.MAS_LOSS_CHOICE if want_choice else 0) | (_lib.MAS_LOSS_GROUP if group_mode is not None else 0)
@@ -121,6 +123,8 @@ def segmented_losses(inputs, targets, superpixels, spmasks, temperature: float, 
     """Like ``segmented_loss_sums`` but normalised on the device: -> tuple indexed by ONE_HOT .. GROUP (0-dim losses)
     and COUNTS ((4,) f64 bucket counts)."""
     trg, spx, mask = _prepare(inputs, targets, superpixels, spmasks)
+    if inputs.dtype != torch.float32:
+        inputs = inputs.float()        # bf16 / fp16 logits (autocast heads): widened once, autograd casts the gradient back
     if trg.shape[2] < inputs.shape[1]:
         raise RuntimeError(f"targets carry {trg.shape[2]} channels, fewer than the {inputs.shape[1]} logit channels")
     flags = (_lib.MAS_LOSS_CHOICE if want_choice else 0) | (_lib.MAS_LOSS_GROUP if group_mode is not None else 0)

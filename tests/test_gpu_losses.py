@@ -176,6 +176,24 @@ def test_reduction_none_returns_sum_and_count_like_the_reference():
         np.testing.assert_allclose(float(mean), float(oracle()), rtol=RTOL)
 
 
+def test_bf16_logits_are_accepted_and_differentiable():
+    """Autocast heads hand over bf16 logits: widened once to fp32 (the kernels compute in fp32), gradient returned in bf16."""
+    from mulactseg_b200 import losses as L
+    n, c, h, w, nseg = 2, 20, 32, 64, 16
+    x = synth.logits(n, c, h, w, "cosine", seed=1).to(torch.bfloat16)
+    spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=2).to(DEV)
+    trg = synth.multihot_targets(n, nseg, c, seed=3, p_ignore=0.0).to(DEV)
+    mask = synth.region_mask(spx, nseg, 0.7, seed=4)
+    group, multi = L.stage1_criterion(types.SimpleNamespace(nseg=nseg, group_ce_temp=0.1, multi_ce_temp=0.1), c - 1)
+    xb = x.to(DEV).requires_grad_(True)
+    xf = x.float().to(DEV).requires_grad_(True)
+    for xin in (xb, xf):
+        ce, mc = multi(xin, trg, spx, mask)
+        (16.0 * ce + 8.0 * mc + group(xin, trg, spx, mask)).backward()
+    assert xb.grad.dtype == torch.bfloat16
+    np.testing.assert_allclose(xb.grad.float().cpu().numpy(), xf.grad.cpu().numpy(), rtol=1e-2, atol=1e-2 * float(xf.grad.abs().max()))
+
+
 def test_shared_pass_never_serves_stale_results():
     from mulactseg_b200 import losses as L
     n, c, h, w, nseg = 2, 8, 16, 32, 8
