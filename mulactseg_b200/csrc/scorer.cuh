@@ -149,7 +149,9 @@ struct Walker {
         }
     }
 
-    __device__ __forceinline__ void row(float (&v)[CMAX][VEC], const int (&id)[VEC]) {
+    // nvalid < VEC: the last pixels of the thread's group lie beyond the image row (they carry another row's data):
+    // they join neither a superpixel nor the softmax sums
+    __device__ __forceinline__ void row(float (&v)[CMAX][VEC], const int (&id)[VEC], int nvalid = VEC) {
         // ---- pure arithmetic first, the VEC pixels in lock step (independent chains interleave)
         float m1[VEC], m2[VEC], bvsb[VEC];
         int top1[VEC];
@@ -181,7 +183,7 @@ struct Walker {
                 }
             }
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) den_a[j] = mas::rcp_approx(den_a[j] + den_b[j]);
+            for (int j = 0; j < VEC; ++j) den_a[j] = j < nvalid ? mas::rcp_approx(den_a[j] + den_b[j]) : 0.f;
 #pragma unroll
             for (int c = 0; c < CMAX; ++c) {
                 float t = pacc[c];
@@ -195,7 +197,7 @@ struct Walker {
         // ids outside [0, S) (crop padding, -1, garbage) become -2: never equal to `cur` (>= -1), never accumulated
         int sid[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) sid[j] = ((unsigned)id[j] < (unsigned)S) ? id[j] : -2;
+        for (int j = 0; j < VEC; ++j) sid[j] = ((unsigned)id[j] < (unsigned)S && j < nvalid) ? id[j] : -2;
         bool touches = false;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) touches |= (sid[j] == cur);

@@ -57,7 +57,7 @@ def test_selectors_match_reference_golden(case):
                                    (5, 20, 24, 200, 64, "jitter"), (3, 22, 37, 132, 150, "jitter"),
                                    (9, 19, 8, 260, 16, "grid")])
 @pytest.mark.parametrize("method", ["my_bvsb_predclsbal_pwr_banignore", "my_bvsb_clsbal_v2"])
-@pytest.mark.parametrize("path", ["tma", "ldg", "abreast"])
+@pytest.mark.parametrize("path", ["tma", "ldg", "abreast", "flat"])
 def test_selectors_match_oracle(shape, method, path, monkeypatch):
     """Every data path of the scorer: TMA ring where rows are 16-byte aligned, the abreast kernel otherwise (or when
     forced), the plain register path when forced ("tma" = the default choice for the shape)."""
@@ -159,7 +159,7 @@ def test_voc_size_properties(shape):
     assert float(score[dominant == c - 1].abs().max() if (dominant == c - 1).any() else 0.0) == 0.0
 
 
-@pytest.mark.parametrize("path", ["tma", "ldg", "abreast"])
+@pytest.mark.parametrize("path", ["tma", "ldg", "abreast", "flat"])
 @pytest.mark.parametrize("shape", [(11, 19, 24, 128, 40, 1), (21, 22, 37, 132, 150, 2), (8, 6, 9, 33, 7, 3)])
 def test_grouped_launches_equal_single_launches(shape, path, monkeypatch):
     """Several loader batches (separate allocations, short last batch, more batches than one launch takes) folded by
@@ -228,7 +228,7 @@ def test_ids_outside_range_are_ignored_and_empty_batch():
     stats.add_batch(0, logits[:0], spx[:0], 1.0)  # empty batch is a no-op
 
 
-@pytest.mark.parametrize("path", ["tma", "ldg", "abreast"])
+@pytest.mark.parametrize("path", ["tma", "ldg", "abreast", "flat"])
 @pytest.mark.parametrize("bad", [-1, -7, 2 ** 31 - 1, "nseg"])
 def test_invalid_ids_before_valid_ones_do_not_leak(path, bad, monkeypatch):
     """A thread that meets out-of-range ids BEFORE its first valid superpixel (top rows of -1 / pad / garbage) must not
