@@ -7,6 +7,16 @@ class CriterionMixin:
     def get_criterion(self):
         self.group_multi_loss, self.multi_pos_loss = stage1_criterion(self.args, self.num_classes, voc=False)
 
+    def train_impl(self, total_itrs, val_period):
+        """The reference's loop (trainer/active.py:73 / active_joint_multi*.py) unchanged; afterwards the partition assertion
+        of the LAST step is raised (it is checked one call late so that no training step waits for the GPU)."""
+        try:
+            return super().train_impl(total_itrs, val_period)
+        finally:
+            check = getattr(getattr(self, "multi_pos_loss", None), "check_partition", None)
+            if check is not None:
+                check()
+
 
 from ._bind import bind  # noqa: E402
 
