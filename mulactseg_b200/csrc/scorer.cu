@@ -205,13 +205,13 @@ bvsb_stats_tma_kernel(const __grid_constant__ TmaMaps maps, const StatsParams p)
         mbar_expect_tx(bar, stage_bytes);
         if (FLAT) {
             const int in_plane = ahead.y * p.W + ahead.strip * kTmaStripPx;
-            int at_elem = (int)((long long)local * p.seg_stride[ahead_seg]) + in_plane;
+            int at_elem = (int)((long long)local * p.seg_stride[ahead_seg]) + in_plane + p.seg_logit_skew[ahead_seg];
             const int plane = p.H * p.W;
             for (int c = 0; c < C; ++c) {
                 tma_load_1d(dst + (uint32_t)c * plane_bytes, &maps.logits[ahead_seg], bar, at_elem, policy);
                 at_elem += plane;
             }
-            tma_load_1d(dst + (uint32_t)C * plane_bytes, &maps.ids[ahead_seg], bar, local * plane + in_plane, policy);
+            tma_load_1d(dst + (uint32_t)C * plane_bytes, &maps.ids[ahead_seg], bar, local * plane + in_plane + p.seg_id_skew[ahead_seg], policy);
         } else {
             tma_load_4d(dst, &maps.logits[ahead_seg], bar, ahead.strip * kTmaStripPx, ahead.y, 0, local, policy);
             tma_load_3d(dst + (uint32_t)C * plane_bytes, &maps.ids[ahead_seg], bar, ahead.strip * kTmaStripPx, ahead.y, local, policy);
@@ -365,18 +365,24 @@ cudaError_t launch_tma(StatsParams p, cudaStream_t stream, bool* unsupported) {
     for (int g = 0; g < p.n_seg; ++g) {
         const cuuint64_t n_seg_img = (cuuint64_t)(p.seg_first[g + 1] - p.seg_first[g]);
         if (FLAT) {
-            // one flat 1-D tensor per segment; box coordinates are signed 32-bit element offsets
-            const cuuint64_t n_logit = (n_seg_img - 1) * (cuuint64_t)p.seg_stride[g] + (cuuint64_t)p.C * p.H * p.W;
-            const cuuint64_t n_id = n_seg_img * (cuuint64_t)p.H * p.W;
-            if (n_logit >= (1ull << 31) - kTmaStripPx) return cudaSuccess;
+            // one flat 1-D tensor per segment; box coordinates are signed 32-bit element offsets.  The map base must be
+            // 16-byte aligned: it is the segment pointer rounded down, the remainder goes into every coordinate.
+            const uintptr_t lp = (uintptr_t)p.seg_logits[g], ip = (uintptr_t)p.seg_ids[g];
+            p.seg_logit_skew[g] = (int)((lp & 15) / elt);
+            p.seg_id_skew[g] = (int)((ip & 15) / 4);
+            void* lbase = reinterpret_cast<void*>(lp & ~(uintptr_t)15);
+            void* ibase = reinterpret_cast<void*>(ip & ~(uintptr_t)15);
+            const cuuint64_t n_logit = (n_seg_img - 1) * (cuuint64_t)p.seg_stride[g] + (cuuint64_t)p.C * p.H * p.W + p.seg_logit_skew[g];
+            const cuuint64_t n_id = n_seg_img * (cuuint64_t)p.H * p.W + p.seg_id_skew[g];
+            if (n_logit >= (1ull << 31) - kTmaStripPx || (lp % elt) != 0 || (ip % 4) != 0) return cudaSuccess;
             const cuuint64_t stride_unused[1] = {0};
             const cuuint32_t box[1] = {kTmaStripPx}, estr[1] = {1};
             const cuuint64_t dims_l[1] = {n_logit}, dims_i[1] = {n_id};
             if (encode(&maps.logits[g], elt == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 1,
-                       const_cast<void*>(p.seg_logits[g]), dims_l, stride_unused, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       lbase, dims_l, stride_unused, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return cudaSuccess;
-            if (encode(&maps.ids[g], CU_TENSOR_MAP_DATA_TYPE_INT32, 1, const_cast<int32_t*>(p.seg_ids[g]), dims_i, stride_unused, box, estr,
+            if (encode(&maps.ids[g], CU_TENSOR_MAP_DATA_TYPE_INT32, 1, ibase, dims_i, stride_unused, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return cudaSuccess;
@@ -500,7 +506,7 @@ extern "C" int mas_bvsb_segment_stats_multi_dev(int n_segments, const void* cons
         p.seg_first[k + 1] = p.n_img;
         vec4 = vec4 && (stride % 4 == 0) && (((uintptr_t)logits[g]) % (4 * elt) == 0) && (((uintptr_t)ids[g]) % 16 == 0);
         tma_ok = tma_ok && ((stride * elt) % 16 == 0) && (((uintptr_t)logits[g]) % 16 == 0);
-        flat_ok = flat_ok && (((uintptr_t)logits[g]) % 16 == 0) && (((uintptr_t)ids[g]) % 16 == 0);
+        flat_ok = flat_ok && (((uintptr_t)logits[g]) % elt == 0) && (((uintptr_t)ids[g]) % 4 == 0);
     }
     if (p.n_img == 0) return 0;
     for (int g = p.n_seg; g < kMaxSeg; ++g) {
@@ -522,6 +528,7 @@ extern "C" int mas_bvsb_segment_stats_multi_dev(int n_segments, const void* cons
     p.strips = 0; p.total_rows = 0; p.stages = 0;
     p.cls_sum = cls_sum; p.cls_cnt = cls_cnt; p.prob_sum = prob_sum;
     p.h_in = 0; p.w_in = 0; p.ry = 1.f; p.rx = 1.f;
+    for (int g = 0; g < kMaxSeg; ++g) { p.seg_logit_skew[g] = 0; p.seg_id_skew[g] = 0; }
 
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
@@ -570,6 +577,7 @@ extern "C" int mas_bvsb_segment_stats_lowres_dev(const void* logits, int logits_
     p.strips = 0; p.total_rows = 0; p.stages = 0;
     p.cls_sum = cls_sum; p.cls_cnt = cls_cnt; p.prob_sum = prob_sum;
     p.h_in = height_in; p.w_in = width_in;
+    for (int g = 0; g < kMaxSeg; ++g) { p.seg_logit_skew[g] = 0; p.seg_id_skew[g] = 0; }
     // torch's area_pixel_compute_scale<float>(input, output, align_corners=false, no scale factor): (float)input / output
     p.ry = (float)height_in / (float)height; p.rx = (float)width_in / (float)width;
     const bool vec4 = (width % 4 == 0) && (((uintptr_t)ids) % 16 == 0);       // only the id map is read with 128-bit loads

@@ -20,6 +20,8 @@ struct StatsParams {
     const int32_t* seg_ids[kMaxSeg];
     long long seg_stride[kMaxSeg];   // elements between images of the segment's logits
     int seg_first[kMaxSeg + 1];      // first image of segment g; seg_first[n_seg] = n_img
+    int seg_logit_skew[kMaxSeg];     // flat TMA path: elements between the 16-byte-aligned map base and the segment's first logit
+    int seg_id_skew[kMaxSeg];        //                the same for the id map
     int n_seg;
     int n_img, C, H, W, S;
     float scale;             // log2(e) / T

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import PoolSet, assert_scores_close, batches, fake_trainer, selector_args
+from helpers import PoolSet, assert_scores_close, batches, fake_trainer, selector_args, tie_free
 from mulactseg_b200 import synth
 from oracle import acquisition as oa
 
@@ -74,6 +74,28 @@ def test_selectors_match_oracle(shape, method, path, monkeypatch):
     assert_scores_close(score.numpy(), ref.numpy(), "pwr" not in method, str(shape))
     hist = oa.region_histograms(pool, nseg, 0.1)
     np.testing.assert_array_equal(stats.cls_cnt.cpu().numpy().astype(np.int64), hist.numpy())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_unaligned_rows_and_unaligned_batch_pointers(dtype):
+    """Odd width and odd plane size (every plane / row has its own alignment phase) with batches that are single-image SLICES
+    of one allocation, so their base pointers are only element-aligned: the flat 1-D TMA path rounds the map base down and
+    skews the box coordinates; the last pixel group of a row is partly beyond the row."""
+    from mulactseg_b200 import acquisition as acq
+    n, c, h, w, nseg = 5, 22, 37, 41, 12
+    logits = tie_free(synth.logits(n, c, h, w, "cosine", seed=8), 0.1, bump=0.05, dtype=dtype if dtype != torch.float32 else None)
+    spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=9)
+    x, ids = logits.to(DEV, dtype), spx.to(DEV, torch.int32)
+    assert x[1:2].data_ptr() % 16 != 0 or x[3:4].data_ptr() % 16 != 0
+    spec = acq.SELECTORS["my_bvsb_predclsbal_pwr_banignore"]
+    stats = acq.RegionStats(n, nseg, c, DEV, need_prob=True)
+    for i in range(n):
+        stats.add_batch(i, x[i:i + 1], ids[i:i + 1], 0.1)
+    score, _ = acq.finalize(stats, spec, 12.0, 1)
+    pool = batches(logits.float(), spx, 1)
+    ref = oa.scores_predclsbal_pwr(pool, nseg, 0.1, 12.0, ban_ignore=True)
+    np.testing.assert_array_equal(stats.cls_cnt.cpu().numpy().astype(np.int64), oa.region_histograms(pool, nseg, 0.1).numpy())
+    assert_scores_close(score.cpu().numpy(), ref.numpy(), False, str(dtype))
 
 
 def test_bf16_logits_match_oracle_on_rounded_inputs():
