@@ -549,7 +549,7 @@ def run_acquisition(ctx: Ctx, wl: Workload, n_loc: int, steps: int, warmup: int,
     launch_ms = float(np.mean(dur)) / n_launch
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
     peak, peak_src = peaks()
-    vec = "tma" if (wl.W * wl.elt) % 16 == 0 else "tma_flat1d"
+    vec = "tma" if (wl.W * wl.elt) % 16 == 0 else "abreast"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": committed_traffic("r1_v7_scorer_tma_c19_12img_full.txt") if wl.key == "cityscapes" else None,
                 "kernel": f"bvsb_stats_{vec}_kernel<{wl.C},{wl.dtype},prob>",

@@ -140,13 +140,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
         : "memory");
 }
 
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int x, uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.tensor.1d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%3}], [%2], %4;" ::"r"(dst), "l"(tm), "r"(bar), "r"(x), "l"(policy)
-        : "memory");
-}
-
 // Shared memory of the TMA kernel (dynamic, 128-byte aligned):
 //   [warps][stages] stage = { T logits[C][128] ; int32 ids[128] }     filled by TMA
 //   [C][threads] uint2                                                private accumulation columns
@@ -156,12 +149,7 @@ struct TmaMaps {     // one pair of tensor maps per segment
     CUtensorMap ids[kMaxSeg];
 };
 
-// FLAT: rows that are not 16-byte aligned (513-pixel VOC crops; odd plane size, so every plane has its own phase).  Tensor
-// maps need 16-byte global strides, but the COORDINATE of a box along the innermost dimension may be any element: each
-// segment is described as ONE flat 1-D tensor and a strip row is fetched as C' + 1 boxes of 128 elements starting at
-// element (image, plane c, y, x0) -- the same ring, stages and walker as the aligned case, one bulk copy per plane.  The
-// last pixels of a row's last group may lie beyond the row (W % 4 != 0): they are masked out of the walker.
-template <int CMAX, bool EXACT, bool NEED_PROB, typename T, bool FLAT>
+template <int CMAX, bool EXACT, bool NEED_PROB, typename T>
 __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1)
 bvsb_stats_tma_kernel(const __grid_constant__ TmaMaps maps, const StatsParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -203,19 +191,8 @@ bvsb_stats_tma_kernel(const __grid_constant__ TmaMaps maps, const StatsParams p)
         const uint32_t dst = smem_u32(my_stages + (size_t)s * stage_bytes);
         const int local = ahead.img - p.seg_first[ahead_seg];
         mbar_expect_tx(bar, stage_bytes);
-        if (FLAT) {
-            const int in_plane = ahead.y * p.W + ahead.strip * kTmaStripPx;
-            int at_elem = (int)((long long)local * p.seg_stride[ahead_seg]) + in_plane + p.seg_logit_skew[ahead_seg];
-            const int plane = p.H * p.W;
-            for (int c = 0; c < C; ++c) {
-                tma_load_1d(dst + (uint32_t)c * plane_bytes, &maps.logits[ahead_seg], bar, at_elem, policy);
-                at_elem += plane;
-            }
-            tma_load_1d(dst + (uint32_t)C * plane_bytes, &maps.ids[ahead_seg], bar, local * plane + in_plane + p.seg_id_skew[ahead_seg], policy);
-        } else {
-            tma_load_4d(dst, &maps.logits[ahead_seg], bar, ahead.strip * kTmaStripPx, ahead.y, 0, local, policy);
-            tma_load_3d(dst + (uint32_t)C * plane_bytes, &maps.ids[ahead_seg], bar, ahead.strip * kTmaStripPx, ahead.y, local, policy);
-        }
+        tma_load_4d(dst, &maps.logits[ahead_seg], bar, ahead.strip * kTmaStripPx, ahead.y, 0, local, policy);
+        tma_load_3d(dst + (uint32_t)C * plane_bytes, &maps.ids[ahead_seg], bar, ahead.strip * kTmaStripPx, ahead.y, local, policy);
         if (ahead.advance(p.strips, p.H) == 2 && ahead_seg + 1 < p.n_seg && ahead.img >= p.seg_first[ahead_seg + 1]) ++ahead_seg;
         ++issued;
     };
@@ -225,7 +202,6 @@ bvsb_stats_tma_kernel(const __grid_constant__ TmaMaps maps, const StatsParams p)
 
     w.img_region = (long long)at.img * p.S;
     bool active = (at.strip * kTmaStripPx + lane * 4) < p.W;
-    int nvalid = FLAT ? min(4, p.W - (at.strip * kTmaStripPx + lane * 4)) : 4;
     int s = 0;
     uint32_t parity = 0;
     for (long long r = r0; r < r1; ++r) {
@@ -247,7 +223,7 @@ bvsb_stats_tma_kernel(const __grid_constant__ TmaMaps maps, const StatsParams p)
                     for (int j = 0; j < 4; ++j) v[c][j] = -INFINITY;
                 }
             }
-            if (FLAT) w.row(v, id, nvalid); else w.row(v, id);
+            w.row(v, id);
         }
         __syncwarp();   // every lane is done with stage s (its loads fed the column updates above)
         if (lane == 0 && issued < r1) {
@@ -260,7 +236,6 @@ bvsb_stats_tma_kernel(const __grid_constant__ TmaMaps maps, const StatsParams p)
         const int step = at.advance(p.strips, p.H);
         if (step != 0) {
             active = (at.strip * kTmaStripPx + lane * 4) < p.W;
-            if (FLAT) nvalid = min(4, p.W - (at.strip * kTmaStripPx + lane * 4));
             if (step == 2) {
                 w.flush();
                 w.flush_prob(p.prob_sum, img_done, lane);
@@ -328,7 +303,7 @@ cudaError_t launch_ldg(StatsParams p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-template <int CMAX, bool EXACT, bool NEED_PROB, typename T, bool FLAT>
+template <int CMAX, bool EXACT, bool NEED_PROB, typename T>
 cudaError_t launch_tma(StatsParams p, cudaStream_t stream, bool* unsupported) {
     *unsupported = true;
     EncodeTiledFn encode = encode_tiled();
@@ -364,30 +339,6 @@ cudaError_t launch_tma(StatsParams p, cudaStream_t stream, bool* unsupported) {
     TmaMaps maps;
     for (int g = 0; g < p.n_seg; ++g) {
         const cuuint64_t n_seg_img = (cuuint64_t)(p.seg_first[g + 1] - p.seg_first[g]);
-        if (FLAT) {
-            // one flat 1-D tensor per segment; box coordinates are signed 32-bit element offsets.  The map base must be
-            // 16-byte aligned: it is the segment pointer rounded down, the remainder goes into every coordinate.
-            const uintptr_t lp = (uintptr_t)p.seg_logits[g], ip = (uintptr_t)p.seg_ids[g];
-            p.seg_logit_skew[g] = (int)((lp & 15) / elt);
-            p.seg_id_skew[g] = (int)((ip & 15) / 4);
-            void* lbase = reinterpret_cast<void*>(lp & ~(uintptr_t)15);
-            void* ibase = reinterpret_cast<void*>(ip & ~(uintptr_t)15);
-            const cuuint64_t n_logit = (n_seg_img - 1) * (cuuint64_t)p.seg_stride[g] + (cuuint64_t)p.C * p.H * p.W + p.seg_logit_skew[g];
-            const cuuint64_t n_id = n_seg_img * (cuuint64_t)p.H * p.W + p.seg_id_skew[g];
-            if (n_logit >= (1ull << 31) - kTmaStripPx || (lp % elt) != 0 || (ip % 4) != 0) return cudaSuccess;
-            const cuuint64_t stride_unused[1] = {0};
-            const cuuint32_t box[1] = {kTmaStripPx}, estr[1] = {1};
-            const cuuint64_t dims_l[1] = {n_logit}, dims_i[1] = {n_id};
-            if (encode(&maps.logits[g], elt == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 1,
-                       lbase, dims_l, stride_unused, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-                return cudaSuccess;
-            if (encode(&maps.ids[g], CU_TENSOR_MAP_DATA_TYPE_INT32, 1, ibase, dims_i, stride_unused, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-                return cudaSuccess;
-            continue;
-        }
         {
             const cuuint64_t dims[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.C, n_seg_img};
             const cuuint64_t strides[3] = {(cuuint64_t)p.W * elt, (cuuint64_t)p.H * p.W * elt, (cuuint64_t)p.seg_stride[g] * elt};
@@ -413,7 +364,7 @@ cudaError_t launch_tma(StatsParams p, cudaStream_t stream, bool* unsupported) {
     for (int g = p.n_seg; g < kMaxSeg; ++g) { maps.logits[g] = maps.logits[0]; maps.ids[g] = maps.ids[0]; }
     *unsupported = false;
 
-    auto kernel = bvsb_stats_tma_kernel<CMAX, EXACT, NEED_PROB, T, FLAT>;
+    auto kernel = bvsb_stats_tma_kernel<CMAX, EXACT, NEED_PROB, T>;
     static mas::PerDeviceInt configured;      // per instantiation AND device (the attribute is a per-device setting)
     {
         cudaError_t e = mas::opt_in_smem(kernel, configured, (int)max_smem);
@@ -436,21 +387,15 @@ cudaError_t launch_tma(StatsParams p, cudaStream_t stream, bool* unsupported) {
     return cudaGetLastError();
 }
 
-enum Path { kPathLdg1 = 0, kPathLdg4 = 1, kPathTma = 2, kPathAbreast1 = 3, kPathAbreast4 = 4, kPathTmaFlat = 5 };
+enum Path { kPathLdg1 = 0, kPathLdg4 = 1, kPathTma = 2, kPathAbreast1 = 3, kPathAbreast4 = 4 };
 
 template <int CMAX, bool EXACT, bool NEED_PROB, typename T>
 cudaError_t launch_path(const StatsParams& p, int path, cudaStream_t stream) {
     if (path == kPathTma) {
         bool unsupported = false;
-        cudaError_t e = launch_tma<CMAX, EXACT, NEED_PROB, T, false>(p, stream, &unsupported);
+        cudaError_t e = launch_tma<CMAX, EXACT, NEED_PROB, T>(p, stream, &unsupported);
         if (!unsupported) return e;
         path = kPathLdg4;   // driver without tensor-map support / shared memory too small for one warp
-    }
-    if (path == kPathTmaFlat) {
-        bool unsupported = false;
-        cudaError_t e = launch_tma<CMAX, EXACT, NEED_PROB, T, true>(p, stream, &unsupported);
-        if (!unsupported) return e;
-        return launch_abreast(p, 1, false, sizeof(T) == 4 ? MAS_F32 : MAS_BF16, stream);
     }
     if (path == kPathLdg4) return launch_ldg<CMAX, EXACT, 4, NEED_PROB, T>(p, stream);
     return launch_ldg<CMAX, EXACT, 1, NEED_PROB, T>(p, stream);
@@ -492,7 +437,7 @@ extern "C" int mas_bvsb_segment_stats_multi_dev(int n_segments, const void* cons
     p.seg_first[0] = 0;
     // 128-bit (f32) / 64-bit (bf16) row segments need every plane row to start VEC-aligned;
     // TMA additionally needs 16-byte global strides and base addresses -- for EVERY segment of the launch
-    bool vec4 = (width % 4 == 0), tma_ok = ((width * elt) % 16 == 0), flat_ok = true;
+    bool vec4 = (width % 4 == 0), tma_ok = ((width * elt) % 16 == 0);
     for (int g = 0; g < n_segments; ++g) {
         MAS_REQUIRE(n_img_per_segment[g] >= 0, MAS_E_BADARG, "bvsb_segment_stats: negative image count");
         if (n_img_per_segment[g] == 0) continue;
@@ -506,7 +451,6 @@ extern "C" int mas_bvsb_segment_stats_multi_dev(int n_segments, const void* cons
         p.seg_first[k + 1] = p.n_img;
         vec4 = vec4 && (stride % 4 == 0) && (((uintptr_t)logits[g]) % (4 * elt) == 0) && (((uintptr_t)ids[g]) % 16 == 0);
         tma_ok = tma_ok && ((stride * elt) % 16 == 0) && (((uintptr_t)logits[g]) % 16 == 0);
-        flat_ok = flat_ok && (((uintptr_t)logits[g]) % elt == 0) && (((uintptr_t)ids[g]) % 4 == 0);
     }
     if (p.n_img == 0) return 0;
     for (int g = p.n_seg; g < kMaxSeg; ++g) {
@@ -515,20 +459,17 @@ extern "C" int mas_bvsb_segment_stats_multi_dev(int n_segments, const void* cons
     }
     MAS_REQUIRE((long long)p.n_img * ((width + 31) / 32) * height < (1ll << 40), MAS_E_RANGE, "bvsb_segment_stats: too many rows");
     tma_ok = tma_ok && vec4;
-    // default: TMA ring with 4-D boxes when every row is 16-byte aligned; else the same ring fed by flat 1-D boxes (needs
-    // only 16-byte aligned segment bases); else the abreast kernel (adjacent strips per CTA)
-    int path = tma_ok ? kPathTma : (flat_ok ? kPathTmaFlat : (vec4 ? kPathAbreast4 : kPathAbreast1));
-    const char* forced = getenv("MAS_SCORER_PATH");   // development / test switch: "ldg" = plain register path, "abreast", "flat"
+    // default: TMA ring when every row is 16-byte aligned, else the abreast kernel (adjacent strips per CTA + L1 prefetch)
+    int path = tma_ok ? kPathTma : (vec4 ? kPathAbreast4 : kPathAbreast1);
+    const char* forced = getenv("MAS_SCORER_PATH");   // development / test switch: "ldg" = plain register path, "abreast"
     if (forced && forced[0] == 'l') path = vec4 ? kPathLdg4 : kPathLdg1;
     if (forced && forced[0] == 'a') path = vec4 ? kPathAbreast4 : kPathAbreast1;
-    if (forced && forced[0] == 'f' && flat_ok) path = kPathTmaFlat;
 
     p.C = channels; p.H = height; p.W = width; p.S = nseg;
     p.scale = 1.4426950408889634f / temperature;
     p.strips = 0; p.total_rows = 0; p.stages = 0;
     p.cls_sum = cls_sum; p.cls_cnt = cls_cnt; p.prob_sum = prob_sum;
     p.h_in = 0; p.w_in = 0; p.ry = 1.f; p.rx = 1.f;
-    for (int g = 0; g < kMaxSeg; ++g) { p.seg_logit_skew[g] = 0; p.seg_id_skew[g] = 0; }
 
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
@@ -577,7 +518,6 @@ extern "C" int mas_bvsb_segment_stats_lowres_dev(const void* logits, int logits_
     p.strips = 0; p.total_rows = 0; p.stages = 0;
     p.cls_sum = cls_sum; p.cls_cnt = cls_cnt; p.prob_sum = prob_sum;
     p.h_in = height_in; p.w_in = width_in;
-    for (int g = 0; g < kMaxSeg; ++g) { p.seg_logit_skew[g] = 0; p.seg_id_skew[g] = 0; }
     // torch's area_pixel_compute_scale<float>(input, output, align_corners=false, no scale factor): (float)input / output
     p.ry = (float)height_in / (float)height; p.rx = (float)width_in / (float)width;
     const bool vec4 = (width % 4 == 0) && (((uintptr_t)ids) % 16 == 0);       // only the id map is read with 128-bit loads

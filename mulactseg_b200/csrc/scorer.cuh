@@ -20,8 +20,6 @@ struct StatsParams {
     const int32_t* seg_ids[kMaxSeg];
     long long seg_stride[kMaxSeg];   // elements between images of the segment's logits
     int seg_first[kMaxSeg + 1];      // first image of segment g; seg_first[n_seg] = n_img
-    int seg_logit_skew[kMaxSeg];     // flat TMA path: elements between the 16-byte-aligned map base and the segment's first logit
-    int seg_id_skew[kMaxSeg];        //                the same for the id map
     int n_seg;
     int n_img, C, H, W, S;
     float scale;             // log2(e) / T
@@ -151,9 +149,7 @@ struct Walker {
         }
     }
 
-    // nvalid < VEC: the last pixels of the thread's group lie beyond the image row (they carry another row's data):
-    // they join neither a superpixel nor the softmax sums
-    __device__ __forceinline__ void row(float (&v)[CMAX][VEC], const int (&id)[VEC], int nvalid = VEC) {
+    __device__ __forceinline__ void row(float (&v)[CMAX][VEC], const int (&id)[VEC]) {
         // ---- pure arithmetic first, the VEC pixels in lock step (independent chains interleave)
         float m1[VEC], m2[VEC], bvsb[VEC];
         int top1[VEC];
@@ -185,7 +181,7 @@ struct Walker {
                 }
             }
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) den_a[j] = j < nvalid ? mas::rcp_approx(den_a[j] + den_b[j]) : 0.f;
+            for (int j = 0; j < VEC; ++j) den_a[j] = mas::rcp_approx(den_a[j] + den_b[j]);
 #pragma unroll
             for (int c = 0; c < CMAX; ++c) {
                 float t = pacc[c];
@@ -199,7 +195,7 @@ struct Walker {
         // ids outside [0, S) (crop padding, -1, garbage) become -2: never equal to `cur` (>= -1), never accumulated
         int sid[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) sid[j] = ((unsigned)id[j] < (unsigned)S && j < nvalid) ? id[j] : -2;
+        for (int j = 0; j < VEC; ++j) sid[j] = ((unsigned)id[j] < (unsigned)S) ? id[j] : -2;
         bool touches = false;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) touches |= (sid[j] == cur);

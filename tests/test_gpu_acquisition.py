@@ -57,7 +57,7 @@ def test_selectors_match_reference_golden(case):
                                    (5, 20, 24, 200, 64, "jitter"), (3, 22, 37, 132, 150, "jitter"),
                                    (9, 19, 8, 260, 16, "grid")])
 @pytest.mark.parametrize("method", ["my_bvsb_predclsbal_pwr_banignore", "my_bvsb_clsbal_v2"])
-@pytest.mark.parametrize("path", ["tma", "ldg", "abreast", "flat"])
+@pytest.mark.parametrize("path", ["tma", "ldg", "abreast"])
 def test_selectors_match_oracle(shape, method, path, monkeypatch):
     """Every data path of the scorer: TMA ring where rows are 16-byte aligned, the abreast kernel otherwise (or when
     forced), the plain register path when forced ("tma" = the default choice for the shape)."""
@@ -79,8 +79,7 @@ def test_selectors_match_oracle(shape, method, path, monkeypatch):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_unaligned_rows_and_unaligned_batch_pointers(dtype):
     """Odd width and odd plane size (every plane / row has its own alignment phase) with batches that are single-image SLICES
-    of one allocation, so their base pointers are only element-aligned: the flat 1-D TMA path rounds the map base down and
-    skews the box coordinates; the last pixel group of a row is partly beyond the row."""
+    of one allocation, so their base pointers are only element-aligned: the abreast kernel (scalar loads) takes them."""
     from mulactseg_b200 import acquisition as acq
     n, c, h, w, nseg = 5, 22, 37, 41, 12
     logits = tie_free(synth.logits(n, c, h, w, "cosine", seed=8), 0.1, bump=0.05, dtype=dtype if dtype != torch.float32 else None)
@@ -181,7 +180,7 @@ def test_voc_size_properties(shape):
     assert float(score[dominant == c - 1].abs().max() if (dominant == c - 1).any() else 0.0) == 0.0
 
 
-@pytest.mark.parametrize("path", ["tma", "ldg", "abreast", "flat"])
+@pytest.mark.parametrize("path", ["tma", "ldg", "abreast"])
 @pytest.mark.parametrize("shape", [(11, 19, 24, 128, 40, 1), (21, 22, 37, 132, 150, 2), (8, 6, 9, 33, 7, 3)])
 def test_grouped_launches_equal_single_launches(shape, path, monkeypatch):
     """Several loader batches (separate allocations, short last batch, more batches than one launch takes) folded by
@@ -250,7 +249,7 @@ def test_ids_outside_range_are_ignored_and_empty_batch():
     stats.add_batch(0, logits[:0], spx[:0], 1.0)  # empty batch is a no-op
 
 
-@pytest.mark.parametrize("path", ["tma", "ldg", "abreast", "flat"])
+@pytest.mark.parametrize("path", ["tma", "ldg", "abreast"])
 @pytest.mark.parametrize("bad", [-1, -7, 2 ** 31 - 1, "nseg"])
 def test_invalid_ids_before_valid_ones_do_not_leak(path, bad, monkeypatch):
     """A thread that meets out-of-range ids BEFORE its first valid superpixel (top rows of -1 / pad / garbage) must not

@@ -129,11 +129,6 @@ def main():
     if "voc513" in sys.argv[1:]:          # short: for ncu
         full_res(res, "voc_crop 513x513x22", 22, 513, 513, 150, 64, ["default"])
         return
-    if "flat" in sys.argv[1:]:            # unaligned rows: flat 1-D TMA boxes vs the abreast kernel
-        full_res(res, "voc_crop 513x513x22", 22, 513, 513, 150, 512, ["default", "abreast", "ldg"])
-        full_res(res, "voc_crop bf16 513x513x22", 22, 513, 513, 150, 512, ["default", "abreast"], torch.bfloat16)
-        full_res(res, "voc_native 375x500x22", 22, 375, 500, 150, 512, ["default", "flat"])
-        return
     if "lowres" in sys.argv[1:]:
         low_res(res, 19, torch.float32)
         return
