@@ -551,7 +551,7 @@ def run_acquisition(ctx: Ctx, wl: Workload, n_loc: int, steps: int, warmup: int,
     peak, peak_src = peaks()
     vec = "tma" if (wl.W * wl.elt) % 16 == 0 else "abreast"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": committed_traffic("r1_v7_scorer_tma_c19_12img_full.txt") if wl.key == "cityscapes" else None,
+                "traffic": committed_traffic("r2_scorer_tma_c19_12img_full.txt") if wl.key == "cityscapes" else None,
                 "kernel": f"bvsb_stats_{vec}_kernel<{wl.C},{wl.dtype},prob>",
                 "peak_source": peak_src + ", burst copy figure; the kernel runs back to back for the whole phase (see sustained_copy_GBps_this_box)",
                 "bytes_per_launch": int(bytes_per_launch), "mean_launch_ms": launch_ms, "launches_per_step": n_launch,

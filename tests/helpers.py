@@ -72,6 +72,8 @@ def tie_free(logits, temp, bump=0.01, dtype=None, drop_last_too=False):
     result stays exactly representable in it (bf16 inputs); ``drop_last_too``: also tie-free over the first C-1 planes
     (the ``preds[:, :-1]`` view plain my_bvsb reads on predignore nets)."""
     x = logits.float().clone()
+    if dtype is not None:
+        x = x.to(dtype).float()          # the ties that matter are those of the ROUNDED values
     for _ in range(8):
         dirty = False
         for view in ((x, x[:, :-1]) if drop_last_too else (x,)):
