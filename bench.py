@@ -557,7 +557,7 @@ def run_acquisition(ctx: Ctx, wl: Workload, n_loc: int, steps: int, warmup: int,
                 "bytes_per_launch": int(bytes_per_launch), "mean_launch_ms": launch_ms, "launches_per_step": n_launch,
                 "lanes": args.lanes, "images_per_launch": round(n_loc / n_launch, 2),
                 "grouping": f"add_batch per loader batch of {wl.ref_batch}; a launch covers the batches queued until {args.group_mb} MB "
-                            "of logits wait (<= 8 batches)",
+                            "of logits wait (<= 32 batches)",
                 "how": "span of the scoring phase (CUDA events on the caller's stream, fork -> join) / launches",
                 "kernel_share_of_step": float(dur.mean() / ms_step),
                 "scoring_phase_ms_per_step": [round(float(x), 3) for x in dur]}

@@ -86,7 +86,7 @@ int mas_bvsb_segment_stats_dev(const void* logits, int logits_dtype, int64_t ima
  * rows of cls_sum / cls_cnt / prob_sum (sum of n_img_per_segment rows).  Small batches (VOC-sized images) are
  * launch-latency-bound one by one; grouped they stream like one big batch.
  */
-#define MAS_MAX_SEGMENTS 8
+#define MAS_MAX_SEGMENTS 32
 int mas_bvsb_segment_stats_multi_dev(int n_segments, const void* const* logits, int logits_dtype, const int64_t* image_strides,
                                      const int32_t* const* ids, const int* n_img_per_segment, int channels, int height,
                                      int width, int nseg, float temperature, float* cls_sum, int32_t* cls_cnt,

@@ -22,7 +22,7 @@ MAS_GROUP_ALL, MAS_GROUP_ONLYMULTI = 0, 1
 MAS_LOSS_CHOICE, MAS_LOSS_GROUP, MAS_LOSS_EXACT_SOFTMAX = 1, 2, 4
 MAS_MAX_CLASSES = 32
 MAS_MAX_LOSS_CLASSES = 31
-MAS_MAX_SEGMENTS = 8
+MAS_MAX_SEGMENTS = 32
 MAS_THRESHOLD_MEDIAN, MAS_THRESHOLD_MIN = 0, 1
 
 # name -> (restype, argtypes); mirrors include/mulactseg_b200.h one to one

@@ -181,7 +181,7 @@ def test_voc_size_properties(shape):
 
 
 @pytest.mark.parametrize("path", ["tma", "ldg", "abreast"])
-@pytest.mark.parametrize("shape", [(11, 19, 24, 128, 40, 1), (21, 22, 37, 132, 150, 2), (8, 6, 9, 33, 7, 3)])
+@pytest.mark.parametrize("shape", [(11, 19, 24, 128, 40, 1), (21, 22, 37, 132, 150, 2), (8, 6, 9, 33, 7, 3), (70, 5, 8, 64, 6, 1)])
 def test_grouped_launches_equal_single_launches(shape, path, monkeypatch):
     """Several loader batches (separate allocations, short last batch, more batches than one launch takes) folded by
     grouped launches == one launch per batch: identical histograms, sums equal up to the order of the fp32 atomics."""
@@ -198,9 +198,11 @@ def test_grouped_launches_equal_single_launches(shape, path, monkeypatch):
         one.add_batch(first, x, ids, 0.1)
         grouped.add_batch(first, x, ids, 0.1)
         first += x.shape[0]
-    assert one.launches == len(parts) and grouped.launches == len(parts) // 8   # only full groups of 8 went out so far ...
+    from mulactseg_b200 import _lib
+    per = _lib.MAS_MAX_SEGMENTS
+    assert one.launches == len(parts) and grouped.launches == len(parts) // per   # only full groups went out so far ...
     assert torch.equal(one.cls_cnt, grouped.cls_cnt)                     # ... reading a table flushes the rest
-    assert grouped.launches == -(-len(parts) // 8)
+    assert grouped.launches == -(-len(parts) // per)
     np.testing.assert_allclose(grouped.cls_sum.cpu().numpy(), one.cls_sum.cpu().numpy(), rtol=2e-6, atol=1e-7)
     np.testing.assert_allclose(grouped.prob_sum.cpu().numpy(), one.prob_sum.cpu().numpy(), rtol=1e-6)   # fp32 per-thread partials
     # a gap in the image rows or another temperature starts a new launch instead of corrupting the group
