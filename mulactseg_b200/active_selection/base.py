@@ -77,12 +77,16 @@ class RegionSelector(object):
         predignore = "predignore" in getattr(self.args, "method", "")
         if self.spec.ban_ignore:
             assert predignore  # my_bvsb_banignore.py:35
+        # opt-in: a net that exposes ``forward_lowres(images) -> (B, C', h, w)`` -- the head's output BEFORE
+        # the final x4 ``F.interpolate`` of models/segmentation/utils.py:28-34 -- is scored from that tensor, the
+        # interpolation to the id map's size happening inside the kernel (``--b200_lowres`` / args.b200_lowres)
+        lowres = bool(getattr(self.args, "b200_lowres", False)) and hasattr(model, "forward_lowres")
         stats, first = None, 0
         with torch.no_grad():
             for batch in loader:
                 images = batch["images"].to(device, dtype=torch.float32, non_blocking=True)
                 spx = batch["spx"].to(torch.int32).to(device, non_blocking=True)
-                preds = model(images)                      # (B, C', H, W) -- stays PyTorch
+                preds = model.forward_lowres(images) if lowres else model(images)      # (B, C', H, W) -- stays PyTorch
                 if preds.dtype not in (torch.float32, torch.bfloat16):
                     preds = preds.float()                  # fp16 / fp64 heads: the reference's ops take any float dtype
                 b_, c_, h_, w_ = preds.shape
@@ -93,7 +97,10 @@ class RegionSelector(object):
                 if stats is None:
                     stats = acquisition.RegionStats(hi - lo, self.num_superpixels, preds.shape[1], device,
                                                     need_prob=self.spec.weighting == "predclsbal")
-                stats.add_batch(first, preds, spx, self.temperature)
+                if lowres:
+                    stats.add_batch_lowres(first, preds.contiguous(), spx, self.temperature)
+                else:
+                    stats.add_batch(first, preds, spx, self.temperature)
                 first += preds.shape[0]
         if stats is None:
             raise RuntimeError("empty pool shard: fewer pool images than ranks")

@@ -513,3 +513,32 @@ def test_lowres_entry_matches_oracle_on_the_interpolated_logits(shape):
     score_full, _ = acq.finalize(stats_full, spec, 6.0, 2)
     np.testing.assert_allclose(score.cpu().numpy()[safe], score_full.cpu().numpy()[safe], rtol=1e-5, atol=1e-12)
     np.testing.assert_allclose(stats.prob_sum.cpu().numpy(), stats_full.prob_sum.cpu().numpy(), rtol=1e-5)
+
+
+def test_selector_plugin_scores_from_the_low_resolution_head_when_asked():
+    """RegionSelector with args.b200_lowres and a net exposing forward_lowres: same scores (1e-5) as the default path on
+    the up-sampled logits, without the up-sampled tensor."""
+    import types
+    from mulactseg_b200.active_selection import my_bvsb_predclsbal_pwr as plugin
+    n, c, h, w, nseg = 4, 19, 64, 128, 32
+    low = synth.logits(n, c, h // 4, w // 4, "cosine", seed=3)
+    spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=4)
+    im_idx, suppix = synth.pool_lists(n, nseg, spx)
+
+    class Net:
+        def eval(self):
+            return self
+
+        def forward_lowres(self, x):
+            return x
+
+        def __call__(self, x):
+            return torch.nn.functional.interpolate(x, size=(h, w), mode="bilinear", align_corners=False)
+
+    pool = PoolSet(low, spx, im_idx, suppix)        # the 'images' handed to the fake net are the low-resolution logits
+    trainer = types.SimpleNamespace(net=Net(), device=torch.device(DEV), model_save_dir="/tmp", selection_iter=1)
+    args = selector_args("my_bvsb_predclsbal_pwr", nseg, c, False, 0.1, 6.0, 2)
+    full = plugin.RegionSelector(args).score_regions(trainer, pool).scores.cpu().numpy()
+    args.b200_lowres = True
+    fused = plugin.RegionSelector(args).score_regions(trainer, pool).scores.cpu().numpy()
+    np.testing.assert_allclose(fused, full, rtol=1e-5, atol=1e-12)

@@ -152,3 +152,74 @@ def test_selection_and_metrics_random(seed):
     ids = sorted(set(rng.randint(0, nseg2, size=max(1, nseg2 // 2)).tolist()))
     np.testing.assert_array_equal(label_assignment.dominant_target(target, spx, ids, nseg2, c2).numpy(),
                                   om.dominant_target(target.numpy(), spx.numpy(), ids))
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_lowres_scorer_random_shapes(seed):
+    """mas_bvsb_segment_stats_lowres_dev on random source / target sizes (integer and fractional ratios, identity, one low-
+    resolution row or column, odd widths -> scalar id loads) against our own full-resolution kernels fed with
+    F.interpolate(..., 'bilinear', align_corners=False) computed on the GPU; regions with a near-tied pixel are left out."""
+    from mulactseg_b200 import acquisition as acq
+    rng = np.random.RandomState(3000 + seed)
+    n = int(rng.randint(1, 4))
+    c = int(rng.choice([2, 5, 19, 20, 22]))
+    h_in, w_in = int(rng.choice([1, 2, 7, 16, 33])), int(rng.choice([1, 3, 8, 31, 32]))
+    fy, fx = float(rng.choice([1.0, 2.0, 3.977, 4.0])), float(rng.choice([1.0, 2.5, 4.0, 4.0]))
+    h, w = max(h_in, int(round(h_in * fy))), max(w_in, int(round(w_in * fx)))
+    nseg = int(rng.choice([1, 6, 40]))
+    dtype = torch.bfloat16 if seed % 3 == 2 else torch.float32
+    low = synth.logits(n, c, h_in, w_in, "cosine", seed=seed).to(dtype).to(DEV)
+    spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=seed + 1).to(DEV, torch.int32)
+    full = torch.nn.functional.interpolate(low.float(), size=(h, w), mode="bilinear", align_corners=False)
+    a = acq.RegionStats(n, nseg, c, DEV, need_prob=True)
+    b = acq.RegionStats(n, nseg, c, DEV, need_prob=True)
+    a.add_batch_lowres(0, low, spx, 0.1)
+    b.add_batch(0, full, spx, 0.1)
+    top2 = full.topk(2, dim=1).values
+    unsafe_px = (top2[:, 0] - top2[:, 1]) <= 1e-5
+    unsafe = torch.zeros((n, nseg + 1), dtype=torch.bool, device=DEV)
+    for i in range(n):
+        unsafe[i, spx[i][unsafe_px[i]].long()] = True
+    safe = ~unsafe[:, :nseg]
+    msg = f"seed {seed}: n={n} c={c} {h_in}x{w_in} -> {h}x{w} nseg={nseg} {dtype}"
+    assert int(a.cls_cnt.sum()) == n * h * w, msg
+    assert torch.equal(a.cls_cnt[safe], b.cls_cnt[safe]), msg
+    np.testing.assert_allclose(a.cls_sum[safe].cpu().numpy(), b.cls_sum[safe].cpu().numpy(), rtol=2e-5, atol=1e-6, err_msg=msg)
+    np.testing.assert_allclose(a.prob_sum.cpu().numpy(), b.prob_sum.cpu().numpy(), rtol=1e-5, atol=1e-6, err_msg=msg)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_loss_step_random_masks_and_shapes(seed):
+    """The whole-step entry points (active-tile list, zero sweep, one call per direction) on awkward shapes and masks --
+    empty, full, a single pixel, odd widths (no 128-bit zero stores), every density around the sparse / dense switch --
+    against the oracle: three losses and the dense gradient."""
+    from mulactseg_b200 import losses as L
+    rng = np.random.RandomState(4000 + seed)
+    h, w = _rng_shape(rng, 60, 140)
+    n = int(rng.randint(1, 4))
+    c = int(rng.choice([3, 8, 20, 21]))
+    nseg = int(rng.choice([1, 4, 30]))
+    rho = float(rng.choice([0.0, 0.05, 0.3, 0.6, 1.0]))
+    x = synth.logits(n, c, h, w, "cosine", seed=seed)
+    spx = synth.pad_border(synth.superpixel_map(n, h, w, nseg, "jitter", seed=seed + 1), nseg, int(rng.randint(0, 3)))
+    trg = synth.multihot_targets(n, nseg, c, seed=seed + 2, p_extra=0.2, p_ignore=0.0)
+    mask = synth.region_mask(spx, nseg, rho, seed=seed + 3)
+    if seed == 0:
+        mask[:] = False
+        mask[0, h // 2, w // 2] = bool(spx[0, h // 2, w // 2] < nseg)
+    xr = x.clone().requires_grad_(True)
+    total_ref, parts_ref = olo.stage1_total(xr, trg, spx, mask, nseg, 0.1, 0.1)
+    if torch.is_tensor(total_ref) and total_ref.requires_grad:
+        total_ref.backward()
+    ref_grad = xr.grad.numpy() if xr.grad is not None else np.zeros(x.shape, dtype=np.float32)
+    group, multi = L.stage1_criterion(types.SimpleNamespace(nseg=nseg, group_ce_temp=0.1, multi_ce_temp=0.1), c - 1)
+    xd = x.to(DEV).requires_grad_(True)
+    td, sd, md = trg.to(DEV), spx.to(DEV), mask.to(DEV)
+    g = group(xd, td, sd, md)
+    ce, mc = multi(xd, td, sd, md)
+    (16.0 * ce + 8.0 * mc + g).backward()
+    msg = f"seed {seed}: n={n} c={c} {h}x{w} nseg={nseg} rho={rho}"
+    as_float = lambda v: float(v.detach()) if torch.is_tensor(v) else float(v)      # noqa: E731
+    np.testing.assert_allclose([ce.item(), mc.item(), g.item()], [as_float(v) for v in parts_ref], rtol=1e-5, atol=1.2e-7, err_msg=msg)
+    np.testing.assert_allclose(xd.grad.cpu().numpy(), ref_grad, rtol=1e-4, atol=1e-5 * max(float(np.abs(ref_grad).max()), 1e-30) + 1e-6,
+                               err_msg=msg)
