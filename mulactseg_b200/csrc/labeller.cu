@@ -23,6 +23,8 @@
 // reading the (F, H, W) features of the touched superpixels once: no tensor cores.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 namespace {
@@ -604,6 +606,177 @@ __global__ void __launch_bounds__(kAssignThreads) proto_propagate_kernel(LabelPa
     }
 }
 
+// ------------------------------------------------------------------------------------------ propagate, tile walk
+// Same result as proto_propagate_kernel, other traversal: the CTA owns a SPATIAL tile (64 px x 8 rows; every warp a
+// 128-byte-aligned 32-pixel row segment), so each feature line the tile needs is requested once and whole -- the
+// per-superpixel CTAs above fetch a line once per superpixel that touches it (1.85x the useful bytes on the bench image;
+// 1.42x is the line-granularity floor).  The pixels of a tile belong to a few superpixels: the CTA forms the UNION of their
+// selected neighbours, walks its prototypes in the reference's order (neighbours by descending id, classes ascending) in
+// batches of kGroup, and every pixel takes part only in the neighbours of ITS superpixel (adjacency bit test when a new
+// neighbour starts) -- the per-pixel sequence of (neighbour, prototype) steps is exactly the one the per-superpixel kernel
+// walks.
+constexpr int kTileW = 64, kTileH = 8, kTileRowsPerWarp = 2;     // 8 warps: 2 across x 4 down, 2 rows each
+
+template <typename FT, bool LOWRES, typename IdT>
+__global__ void __launch_bounds__(kAssignThreads) proto_propagate_tile_kernel(LabelParams p) {
+    extern __shared__ __align__(16) float sproto[];          // [F][kGroup], then tset[words], nset[words]
+    uint32_t* tset = reinterpret_cast<uint32_t*>(sproto + (size_t)p.F * kGroup);
+    uint32_t* nset = tset + p.words;
+    __shared__ ProtoEntry ent[kGroup];
+    __shared__ float ent_thr[kGroup];
+    __shared__ int n_ent, cur_word, cur_s;
+    __shared__ uint32_t cur_bits, cur_cls;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * kTileW + (warp & 1) * 32 + lane;
+    const int y0 = blockIdx.y * kTileH + (warp >> 1) * kTileRowsPerWarp;
+
+    for (int w = threadIdx.x; w < 2 * p.words; w += blockDim.x) tset[w] = 0u;      // tset and nset are contiguous
+    __syncthreads();
+    // this thread's pixels: superpixel id (-1: nothing to do) -- unselected pixels of superpixels with a selected neighbour
+    int tid_[kTileRowsPerWarp], pix[kTileRowsPerWarp];
+#pragma unroll
+    for (int r = 0; r < kTileRowsPerWarp; ++r) {
+        const int y = y0 + r;
+        tid_[r] = -1; pix[r] = -1;
+        if (x < p.W && y < p.H) {
+            const int px = y * p.W + x;
+            const int t = read_id<IdT>(p.ids, (size_t)px, p.S);
+            if (t >= 0 && p.touched[t] && !pixel_selected(p, px, p.info[t])) {
+                tid_[r] = t; pix[r] = px;
+                const uint32_t bit = 1u << (t & 31);
+                if (!(tset[t >> 5] & bit)) atomicOr(&tset[t >> 5], bit);
+            }
+        }
+    }
+    const bool cta_any = __syncthreads_or(tid_[0] >= 0 || tid_[1] >= 0);
+    if (!cta_any) return;
+    // union of the selected neighbours (each superpixel itself included) of the tile's superpixels
+    for (int w = threadIdx.x; w < p.words; w += blockDim.x) {
+        uint32_t acc = 0u;
+        for (int tw = 0; tw < p.words; ++tw) {
+            uint32_t bits = tset[tw];
+            while (bits) {
+                const int t = tw * 32 + (__ffs(bits) - 1);
+                bits &= bits - 1u;
+                acc |= p.adj[(size_t)t * p.words + w] | ((w == (t >> 5)) ? (1u << (t & 31)) : 0u);
+            }
+        }
+        nset[w] = acc & p.svalid[w];
+    }
+    // per-pixel state of the neighbour being evaluated (its prototypes may span two batches)
+    float best[kTileRowsPerWarp];
+    int bestc[kTileRowsPerWarp];
+    bool pass[kTileRowsPerWarp], done[kTileRowsPerWarp], rel[kTileRowsPerWarp];
+#pragma unroll
+    for (int r = 0; r < kTileRowsPerWarp; ++r) { best[r] = -INFINITY; bestc[r] = 255; pass[r] = false; done[r] = tid_[r] < 0; rel[r] = false; }
+    __syncthreads();
+    if (threadIdx.x == 0) { cur_word = p.words; cur_bits = 0u; cur_cls = 0u; cur_s = -1; }
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int n = 0;
+            int w = cur_word, sidx = cur_s;
+            uint32_t nb = cur_bits, cls = cur_cls;
+            while (n < kGroup) {
+                if (cls == 0u) {                     // next neighbour of the union, descending id
+                    while (nb == 0u && w > 0) { --w; nb = nset[w]; }
+                    if (nb == 0u) break;
+                    const int bitpos = 31 - __clz(nb);
+                    nb &= ~(1u << bitpos);
+                    sidx = w * 32 + bitpos;
+                    cls = p.info[sidx] & ~kGroupBit;
+                    if (cls == 0u) continue;
+                    ent[n].first = 1;
+                } else {
+                    ent[n].first = 0;
+                }
+                const int c = __ffs(cls) - 1;
+                cls &= cls - 1u;
+                ent[n].s = sidx; ent[n].c = c;
+                ent_thr[n] = p.thr[(size_t)sidx * p.C + c];
+                ++n;
+            }
+            n_ent = n; cur_word = w; cur_bits = nb; cur_cls = cls; cur_s = sidx;
+        }
+        __syncthreads();
+        const int n = n_ent;
+        if (n == 0) break;
+        stage_entries(p, sproto, ent, n);
+        bool mine_done = true;
+#pragma unroll
+        for (int r = 0; r < kTileRowsPerWarp; ++r) mine_done &= done[r];
+        const bool all_done = __syncthreads_and(mine_done);          // also orders the staging before the reads
+        if (all_done) break;
+#pragma unroll
+        for (int r = 0; r < kTileRowsPerWarp; ++r) {
+            // does this pixel's superpixel meet any neighbour of the batch?  (a neighbour continued from the previous batch
+            // keeps its flag; new ones are tested when they start)
+            bool wanted = false;
+            if (!done[r]) {
+                bool carry = rel[r];
+#pragma unroll
+                for (int g = 0; g < kGroup; ++g) {
+                    if (g < n) {
+                        if (ent[g].first) {
+                            const int s2 = ent[g].s;
+                            carry = s2 == tid_[r] || ((p.adj[(size_t)tid_[r] * p.words + (s2 >> 5)] >> (s2 & 31)) & 1u);
+                        }
+                        wanted |= carry;
+                    }
+                }
+            }
+            if (!__any_sync(0xffffffffu, wanted)) {
+                // nobody in the warp row needs this batch: only the neighbour bookkeeping advances
+                if (!done[r]) {
+#pragma unroll
+                    for (int g = 0; g < kGroup; ++g) {
+                        if (g < n && ent[g].first && !done[r]) {
+                            if (pass[r]) { p.labels[pix[r]] = (uint8_t)bestc[r]; done[r] = true; }
+                            best[r] = -INFINITY; bestc[r] = 255; pass[r] = false;
+                            const int s2 = ent[g].s;
+                            rel[r] = s2 == tid_[r] || ((p.adj[(size_t)tid_[r] * p.words + (s2 >> 5)] >> (s2 & 31)) & 1u);
+                        }
+                    }
+                }
+                continue;
+            }
+            if (!done[r] && wanted) {
+                float acc[kGroup];
+                dot_all<FT, LOWRES>(p, sproto, pix[r], n, acc);
+#pragma unroll
+                for (int g = 0; g < kGroup; ++g) {
+                    if (g < n && !done[r]) {
+                        if (ent[g].first) {              // the previous neighbour is complete: did it pass?
+                            if (pass[r]) { p.labels[pix[r]] = (uint8_t)bestc[r]; done[r] = true; }
+                            best[r] = -INFINITY; bestc[r] = 255; pass[r] = false;
+                            const int s2 = ent[g].s;
+                            rel[r] = s2 == tid_[r] || ((p.adj[(size_t)tid_[r] * p.words + (s2 >> 5)] >> (s2 & 31)) & 1u);
+                        }
+                        if (!done[r] && rel[r]) {
+                            if (acc[g] > best[r] || bestc[r] == 255) { best[r] = acc[g]; bestc[r] = ent[g].c; }
+                            pass[r] |= ent_thr[g] < acc[g];
+                        }
+                    }
+                }
+            } else if (!done[r]) {
+#pragma unroll
+                for (int g = 0; g < kGroup; ++g) {
+                    if (g < n && ent[g].first && !done[r]) {
+                        if (pass[r]) { p.labels[pix[r]] = (uint8_t)bestc[r]; done[r] = true; }
+                        best[r] = -INFINITY; bestc[r] = 255; pass[r] = false;
+                        const int s2 = ent[g].s;
+                        rel[r] = s2 == tid_[r] || ((p.adj[(size_t)tid_[r] * p.words + (s2 >> 5)] >> (s2 & 31)) & 1u);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kTileRowsPerWarp; ++r) {
+        if (!done[r] && pass[r]) p.labels[pix[r]] = (uint8_t)bestc[r];
+    }
+}
+
 // one launch instead of two memsets + the candidate-word kernel: zero the accumulating part of the workspace, fill the
 // label map with 255 ("unlabeled") and build the candidate word of every superpixel (bit c: class c is a candidate of
 // the net's C channels; top bit: the superpixel takes part -- always, or only when multi-hot; same as mas_multihot_info_dev)
@@ -686,7 +859,15 @@ int run_labeller(const LabelParams& p, const Workspace& w, cudaStream_t st) {
     const dim3 grid_sp((unsigned)p.S, kSlices);
     proto_assign_kernel<FT, LOWRES><<<grid_sp, kAssignThreads, smem, st>>>(p);
     proto_threshold_kernel<<<p.S, kAssignThreads, 0, st>>>(p);
-    proto_propagate_kernel<FT, LOWRES><<<grid_sp, kAssignThreads, smem, st>>>(p);
+    {
+        const char* v = getenv("MAS_LABELLER_TILE");        // development switch: "1" = spatial-tile propagate
+        if (v && v[0] == '1') {
+            const dim3 grid_t((unsigned)((p.W + kTileW - 1) / kTileW), (unsigned)((p.H + kTileH - 1) / kTileH));
+            proto_propagate_tile_kernel<FT, LOWRES, IdT><<<grid_t, kAssignThreads, smem + 2 * (size_t)p.words * sizeof(uint32_t), st>>>(p);
+        } else {
+            proto_propagate_kernel<FT, LOWRES><<<grid_sp, kAssignThreads, smem, st>>>(p);
+        }
+    }
     mas::count_launches(7);
     MAS_LAUNCH_OK("prototype labeller kernels");
     return 0;
