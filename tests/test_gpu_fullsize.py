@@ -126,12 +126,16 @@ def test_stage1_losses_match_the_oracle_at_train_crop_size(rho):
     assert float(np.abs(got[2]).max()) == 0.0
 
 
-@pytest.mark.parametrize("shape", [("cityscapes", 1024, 2048, 2048, 20, 256, 0.08, "median", False),
-                                   ("cityscapes_multihot_min", 1024, 2048, 2048, 20, 256, 0.3, "min", True),
-                                   ("voc", 375, 500, 150, 21, 256, 0.3, "median", False)])
-def test_proto_labeller_matches_the_oracle_at_baseline_shapes(shape):
+@pytest.mark.parametrize("shape", [("cityscapes", 1024, 2048, 2048, 20, 256, 0.08, "median", False, ""),
+                                   ("cityscapes_tile_walk", 1024, 2048, 2048, 20, 256, 0.08, "median", False, "1"),
+                                   ("cityscapes_multihot_min", 1024, 2048, 2048, 20, 256, 0.3, "min", True, ""),
+                                   ("voc", 375, 500, 150, 21, 256, 0.3, "median", False, ""),
+                                   ("voc_superpixel_walk", 375, 500, 150, 21, 256, 0.3, "median", False, "0")])
+def test_proto_labeller_matches_the_oracle_at_baseline_shapes(shape, monkeypatch):
     from mulactseg_b200 import labeller
-    name, h, w, nseg, c, ch, rho, thr, only_multihot = shape
+    name, h, w, nseg, c, ch, rho, thr, only_multihot, walk = shape
+    if walk:
+        monkeypatch.setenv("MAS_LABELLER_TILE", walk)
     feats = synth.features(1, ch, h, w, seed=41)
     logits = synth.logits(1, c, h, w, "normal", seed=42, coherent=4)
     spx = synth.superpixel_map(1, h, w, nseg, "jitter", seed=43)

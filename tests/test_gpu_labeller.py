@@ -18,9 +18,11 @@ LAB_KEYS = sorted({k.rsplit("/", 1)[0] for k in LAB.files if k.startswith("eval_
 
 
 @pytest.mark.parametrize("key", LAB_KEYS)
-@pytest.mark.parametrize("id_dtype", [torch.int64, torch.int32])
-def test_proto_labeller_matches_reference_golden(key, id_dtype):
+@pytest.mark.parametrize("id_dtype,walk", [(torch.int64, "1"), (torch.int32, "0")])
+def test_proto_labeller_matches_reference_golden(key, id_dtype, walk, monkeypatch):
+    """Both traversals of the propagate step (spatial tiles / one CTA per superpixel slice) against the reference's labels."""
     import importlib
+    monkeypatch.setenv("MAS_LABELLER_TILE", walk)
     variant, thr, _ = key.split("/")
     mixin = importlib.import_module(f"mulactseg_b200.trainer.{variant}").LabellerMixin
 
@@ -49,9 +51,10 @@ def test_top_labeller_matches_reference_golden():
 @pytest.mark.parametrize("shape", [(40, 56, 20, 7, 32, 0.4, "jitter"), (33, 47, 12, 21, 64, 0.7, "jitter"),
                                    (24, 36, 16, 6, 16, 1.0, "grid"), (20, 24, 30, 5, 8, 0.5, "random"),
                                    (64, 96, 40, 12, 256, 0.15, "jitter")])
-@pytest.mark.parametrize("only_multihot,thr", [(False, "median"), (True, "median"), (False, "min")])
-def test_proto_labeller_matches_oracle(shape, only_multihot, thr):
+@pytest.mark.parametrize("only_multihot,thr,walk", [(False, "median", "0"), (True, "median", "1"), (False, "min", "1"), (False, "median", "1")])
+def test_proto_labeller_matches_oracle(shape, only_multihot, thr, walk, monkeypatch):
     from mulactseg_b200 import labeller
+    monkeypatch.setenv("MAS_LABELLER_TILE", walk)
     h, w, nseg, c, ch, rho, kind = shape
     feats = synth.features(1, ch, h, w, seed=h)
     logits = synth.logits(1, c, h, w, "normal", seed=w, coherent=4)
