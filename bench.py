@@ -519,7 +519,7 @@ def run_acquisition(ctx: Ctx, wl: Workload, n_loc: int, steps: int, warmup: int,
         return out
 
     sampler = ClockSampler(ctx.local) if (rank == 0 and headline) else None     # comes up while the phase breakdown runs
-    phase_ms = phases() if world == 1 else None
+    phase_ms = phases()          # every rank runs it (the collectives inside need all of them); rank 0 reports
     if sampler is not None:
         time.sleep(0.3)
     ctx.sync_all()
