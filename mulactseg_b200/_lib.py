@@ -12,7 +12,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmulactseg_b200.so")
+LIB_PATH = os.environ.get("MULACTSEG_B200_LIB") or os.path.join(_HERE, "lib", "libmulactseg_b200.so")   # override: comparison builds
 
 MAS_F32, MAS_BF16 = 0, 1
 MAS_I32, MAS_I64, MAS_U8 = 0, 1, 2

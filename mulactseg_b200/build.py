@@ -18,11 +18,12 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "csrc", "build")
 LIBDIR = os.path.join(PKG, "lib")
-LIB = os.path.join(LIBDIR, "libmulactseg_b200.so")
+LIB = os.environ.get("MAS_LIB_OUT") or os.path.join(LIBDIR, "libmulactseg_b200.so")      # MAS_LIB_OUT: comparison builds
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
+FLAGS += os.environ.get("MAS_NVCC_EXTRA", "").split()      # development: extra -D switches (comparison builds)
 
 
 def _sources():
@@ -44,7 +45,7 @@ def _compile(src: str) -> str:
     obj = os.path.join(OBJ, f"{os.path.splitext(src)[0]}.{_digest(path)}.o")
     if not os.path.exists(obj):
         for old in os.listdir(OBJ):
-            if old.startswith(os.path.splitext(src)[0] + "."):
+            if old.startswith(os.path.splitext(src)[0] + ".") and not os.environ.get("MAS_LIB_OUT"):
                 os.remove(os.path.join(OBJ, old))
         cmd = [NVCC, *ARCH, *FLAGS, "-c", path, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -58,7 +59,7 @@ def build(verbose: bool = True) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(_compile, _sources()))
-    stamp = os.path.join(OBJ, "link.stamp")
+    stamp = os.path.join(OBJ, "link.stamp" if not os.environ.get("MAS_LIB_OUT") else "link.alt.stamp")
     want = " ".join(os.path.basename(o) for o in objs)
     have = open(stamp).read() if os.path.exists(stamp) else ""
     if want != have or not os.path.exists(LIB):
