@@ -17,39 +17,15 @@
 // Same walking scheme as the scorer (walk.cuh): a thread stays inside one superpixel for many rows and
 // keeps that superpixel's running maxima in a private shared-memory column; global atomicMax only when
 // the superpixel changes.  Backward recomputes the softmax and writes the dense gradient once.
-#include "common.cuh"
+#include "losses.cuh"
 
 #include <stdlib.h>
 
 #include <algorithm>
 
+using namespace mas_loss;
+
 namespace {
-
-constexpr int kThreads = 128;
-constexpr uint32_t kGroupBit = 0x80000000u;
-constexpr float kEps = 1e-8f;
-
-struct LossParams {
-    const float* logits;
-    const void* ids;
-    const uint8_t* mask;
-    const uint32_t* info;
-    int n_img, C, H, W, S;
-    float temp;      // T
-    float inv_temp;  // 1 / T
-    float scale;     // log2(e) / T
-    int do_choice, do_group;
-    int tile_rows;                // rows per tile (<= kTileRows)
-    double* acc;                  // fwd: [0..5] one-hot / multi-hot / empty {sum, count}
-    unsigned long long* gmax;     // (n_img * S * C) packed maxima
-    const float* coef;            // bwd: {w_onehot, w_multihot, w_empty, w_group} = d total / d bucket sum
-    float* grad;
-    // ACTIVE-TILE LIST (mas_multihot_tiles_dev; NULL = walk every tile): 32 px x kListRows tiles that hold a selected pixel
-    const uint32_t* tile_words;   // bit l of word g: tile 32 g + l is active
-    const int* tile_offsets;      // exclusive prefix sum of the popcounts; tile_offsets[n_groups] = number of active tiles
-    int n_groups;
-    int list_mode;                // 1: take tiles from the list (forward always; backward when the image is sparsely selected)
-};
 
 __global__ void multihot_info_kernel(const uint8_t* __restrict__ targets, long long n_regions, int Ct, int C, int group_mode,
                                      uint32_t* __restrict__ info) {
@@ -242,12 +218,7 @@ struct RowPipe {
 // selected pixel plus its prefix sums; both passes then deal the ACTIVE tiles round-robin to their warps (rank -> tile by
 // binary search + bit select: deterministic, unlike an atomic queue), and a sparsely selected batch gets its gradient
 // zeroed by one linear sweep with only the active tiles computed on top.
-constexpr int kListRows = 8;
 constexpr int kSparsePercent = 35;      // backward: list mode when fewer than this share of the tiles is active
-
-__device__ __forceinline__ long long list_tile_count(int n_img, int H, int W) {
-    return (long long)n_img * ((W + 31) / 32) * ((H + kListRows - 1) / kListRows);
-}
 
 // tile of rank r in the active list
 __device__ __forceinline__ long long list_select(const LossParams& p, int r) {
@@ -324,8 +295,8 @@ __global__ void __launch_bounds__(256) tile_scan_kernel(const uint8_t* __restric
 
 // backward, list mode only: one linear sweep zeroes the dense gradient (the active tiles are then computed on top)
 __global__ void __launch_bounds__(256) grad_zero_kernel(float* __restrict__ grad, size_t n, const int* __restrict__ offsets, int n_groups,
-                                                        long long n_tiles) {
-    if ((long long)offsets[n_groups] * 100 >= n_tiles * kSparsePercent) return;      // densely selected: the tile walk fills everything
+                                                        long long n_tiles, int percent) {
+    if ((long long)offsets[n_groups] * 100 >= n_tiles * percent) return;      // densely selected: the tile walk fills everything
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     const size_t head = min(n, (size_t)(((16 - (reinterpret_cast<uintptr_t>(grad) & 15)) & 15) / 4));
     const size_t vecs = (n - head) / 4;
@@ -341,6 +312,7 @@ __global__ void __launch_bounds__(kThreads) multihot_loss_fwd_kernel(const LossP
     // [C][kThreads] u64: running maxima of the thread's current superpixel;  [C][kThreads] f32: softmax numerators of
     // the pixel being processed (registers cannot be indexed by the candidate class; private columns, no conflicts)
     extern __shared__ unsigned long long gcol[];
+    if (dense_regime(p)) return;          // densely selected batch: the strip walk of losses_dense.cu takes it
     const int tid = threadIdx.x, lane = tid & 31;
     const int C = EXACT ? CMAX : p.C;
     unsigned long long* col = gcol + tid;
@@ -481,6 +453,7 @@ __global__ void group_loss_reduce_kernel(const unsigned long long* __restrict__ 
 template <int CMAX, bool EXACT, typename IdT>
 __global__ void __launch_bounds__(kThreads) multihot_loss_bwd_kernel(const LossParams p) {
     extern __shared__ float pst_all[];     // [C][kThreads] softmax numerators of the pixel being processed
+    if (dense_regime(p)) return;          // densely selected batch: the strip walk of losses_dense.cu takes it
     const int C = EXACT ? CMAX : p.C;
     float* pst = pst_all + threadIdx.x;
     const bool do_choice = p.do_choice != 0, do_group = p.do_group != 0;
@@ -496,7 +469,8 @@ __global__ void __launch_bounds__(kThreads) multihot_loss_bwd_kernel(const LossP
     if (p.list_mode) {
         const long long n_list_tiles = list_tile_count(p.n_img, p.H, p.W);
         const long long n_active = __ldg(p.tile_offsets + p.n_groups);
-        if (n_active * 100 < n_list_tiles * kSparsePercent) q.tile_rows = kListRows; else q.list_mode = 0;
+        const int pct = p.dense_percent > 0 ? p.dense_percent : kSparsePercent;
+        if (n_active * 100 < n_list_tiles * pct) q.tile_rows = kListRows; else q.list_mode = 0;
     }
     const bool listed = q.list_mode != 0;
     const long long n_work = listed ? (long long)__ldg(p.tile_offsets + p.n_groups) : n_dense;
@@ -694,7 +668,8 @@ cudaError_t launch_one(LossParams p, bool backward, bool accurate, cudaStream_t 
     if (backward && p.list_mode) {
         const size_t n = (size_t)p.n_img * p.C * p.H * p.W;
         const unsigned zblocks = (unsigned)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)mas::sm_count() * 16);
-        grad_zero_kernel<<<zblocks, 256, 0, stream>>>(p.grad, n, p.tile_offsets, p.n_groups, strips * ((p.H + kListRows - 1) / kListRows));
+        grad_zero_kernel<<<zblocks, 256, 0, stream>>>(p.grad, n, p.tile_offsets, p.n_groups, strips * ((p.H + kListRows - 1) / kListRows),
+                                                      p.dense_percent > 0 ? p.dense_percent : kSparsePercent);
         mas::count_launches(1);
     }
     if (backward) {
@@ -722,7 +697,30 @@ cudaError_t dispatch_channels(const LossParams& p, bool backward, bool accurate,
     return launch_one<31, false, IdT>(p, backward, accurate, stream);
 }
 
-cudaError_t dispatch(const LossParams& p, int ids_dtype, bool backward, bool accurate, cudaStream_t stream) {
+// MAS_LOSS_DENSE: unset = the device picks per batch (needs the active-tile list), 0 = never, 1 = always when the shape
+// allows (tests, comparisons).  MAS_LOSS_DENSE_PCT: share of active tiles from which the dense kernels take over.
+constexpr int kDensePercent = 40;
+
+cudaError_t dispatch(LossParams p, int ids_dtype, bool backward, bool accurate, cudaStream_t stream) {
+    const char* mode_env = getenv("MAS_LOSS_DENSE");
+    const int mode = (mode_env && *mode_env) ? atoi(mode_env) : -1;
+    p.dense_percent = 0;
+    if (!accurate && mode != 0 && (p.list_mode || mode == 1)) {
+        LossParams d = p;
+        if (mode == 1) {
+            d.list_mode = 0;      // runs unconditionally
+        } else {
+            const char* pct_env = getenv("MAS_LOSS_DENSE_PCT");
+            d.dense_percent = (pct_env && *pct_env) ? std::min(100, std::max(1, atoi(pct_env))) : kDensePercent;
+        }
+        bool launched = false;
+        cudaError_t e = launch_dense(d, ids_dtype, backward, stream, &launched);
+        if (e != cudaSuccess) return e;
+        if (launched) {
+            if (mode == 1) return cudaSuccess;
+            p.dense_percent = d.dense_percent;      // the list kernels below leave densely selected batches alone
+        }
+    }
     if (ids_dtype == MAS_I64) return dispatch_channels<long long>(p, backward, accurate, stream);
     return dispatch_channels<int32_t>(p, backward, accurate, stream);
 }

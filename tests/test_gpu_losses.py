@@ -140,8 +140,9 @@ def test_shared_pass_equals_separate_passes_and_trainer_total():
     loss.backward()
     torch.cuda.synchronize()
     launches = _lib.load().mas_kernel_launches() - before
-    # candidate words + active-tile scan + fused forward + group reduce + finish; coefficients + zero sweep + fused backward
-    assert launches == 8
+    # candidate words + active-tile scan + fused forward (dense and list kernels: the device picks, one returns at once) +
+    # group reduce + finish; coefficients + zero sweep + fused backward (dense and list)
+    assert launches == 10
     np.testing.assert_allclose([ce.item(), mc.item(), g.item()], [ce_ref.item(), mc_ref.item(), group_ref.item()], rtol=RTOL)
     np.testing.assert_allclose(loss.item(), total_ref.item(), rtol=RTOL)
     ref_grad = xr.grad.numpy()

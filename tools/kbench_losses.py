@@ -34,7 +34,7 @@ def main():
     trg = synth.multihot_targets(n, nseg, c, seed=3, device=DEV, p_ignore=0.0)
     flags = _lib.MAS_LOSS_CHOICE | _lib.MAS_LOSS_GROUP
     coef = torch.tensor([1e-4, 1e-4, 0.0, 1e-3], device=DEV)
-    for rho in (0.02, 0.08, 0.2, 1.0):
+    for rho in (0.02, 0.08, 0.2, 0.5, 1.0):
         mask = synth.region_mask(spx, nseg, rho, seed=4)
         info = ops.multihot_info(trg, c, _lib.MAS_GROUP_ONLYMULTI)
         turn = [0]
@@ -54,7 +54,15 @@ def main():
 
         t_f0, t_b0 = time_ms(fwd), time_ms(bwd)          # every tile walked (no list)
         use[0] = tiles
-        t_f, t_b = time_ms(fwd), time_ms(bwd)
+        os.environ["MAS_LOSS_DENSE"] = "0"
+        t_f, t_b = time_ms(fwd), time_ms(bwd)                       # active-tile list walk
+        os.environ["MAS_LOSS_DENSE"] = "1"
+        t_fd, t_bd = time_ms(fwd), time_ms(bwd)                     # dense TMA strip walk, forced
+        del os.environ["MAS_LOSS_DENSE"]
+        t_fa, t_ba = time_ms(fwd), time_ms(bwd)                     # the device picks
+        n_groups = (tiles.numel() - 16 - 4) // 8
+        active = int(tiles[16 + 4 * n_groups:].view(torch.int32)[n_groups])
+        total_tiles = n * ((w + 31) // 32) * ((h + 7) // 8)
         t_scan = time_ms(lambda: ops.multihot_tiles(mask))
         zero = torch.empty_like(xs[0])
         t_z = time_ms(lambda: zero.zero_())
@@ -79,7 +87,9 @@ def main():
         host = (time.perf_counter() - t0) / 50 * 1e3        # host time to ENQUEUE a step (no sync inside)
         torch.cuda.synchronize()
         res[f"rho={rho}"] = {"fwd_all_tiles_ms": round(t_f0, 4), "bwd_all_tiles_ms": round(t_b0, 4), "tile_scan_ms": round(t_scan, 4),
-                             "fwd_kernels_ms": round(t_f, 4), "bwd_kernel_ms": round(t_b, 4), "memset_grad_ms": round(t_z, 4),
+                             "fwd_kernels_ms": round(t_f, 4), "bwd_kernel_ms": round(t_b, 4), "fwd_dense_ms": round(t_fd, 4),
+                             "bwd_dense_ms": round(t_bd, 4), "fwd_auto_ms": round(t_fa, 4), "bwd_auto_ms": round(t_ba, 4),
+                             "active_tile_frac": round(active / total_tiles, 4), "memset_grad_ms": round(t_z, 4),
                              "step_ms": round(t_s, 4), "host_enqueue_ms": round(host, 4)}
         print(f"rho={rho}", res[f"rho={rho}"], flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
