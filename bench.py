@@ -783,9 +783,18 @@ def run_labeller(ctx: Ctx, name: str, steps: int):
         return labeller.pseudo_label_generation(None, feats[i], logits[i], trg, mask, spx, check=False)
 
     launches0 = ctx.lib.mas_kernel_launches()
-    ms = time_ms(step, iters=max(steps, 5) * 2)
+    ms_single = time_ms(step, iters=max(steps, 5) * 2)
     launches = (ctx.lib.mas_kernel_launches() - launches0) // (3 + max(steps, 5) * 2)
+    # the call the reference's loop makes: one loader batch per call (the images of a batch run on side streams)
+    bs = n_rot
+    fb, lb = torch.cat(feats), torch.cat(logits)
+    tb, mb, sb = trg.repeat(bs, 1, 1), mask.repeat(bs, 1, 1), spx.repeat(bs, 1, 1)
+    ms = time_ms(lambda: labeller.pseudo_label_generation(None, fb, lb, tb, mb, sb, check=False), iters=max(steps, 5)) / bs
+    out_batch = labeller.pseudo_label_generation(None, fb, lb, tb, mb, sb)
     out_lab = labeller.pseudo_label_generation(None, feats[0], logits[0], trg, mask, spx)
+    batch_equal = all(bool(torch.equal(out_batch[i], labeller.pseudo_label_generation(None, feats[i], logits[i], trg, mask, spx)[0]))
+                      for i in range(bs))
+    del fb, lb
     sel = float(mask.float().mean())
     P = h * w
     # feature columns of selected pixels (assign) + of every unselected pixel of a touched superpixel (propagate, once)
@@ -797,12 +806,15 @@ def run_labeller(ctx: Ctx, name: str, steps: int):
     touched_frac = float(touched[spx[0]].float().mean())
     alg = P * (1 + 8) * 3 + sel * P * c * 4 + touched_frac * P * 256 * 4 + P
     peak, _ = peaks()
-    out = {"workload": f"configs[4]: cosplbl_prop prototype labeller, one {h}x{w} image, 256-d features, {c} classes, {nseg} superpixels, rho={rho}",
+    out = {"workload": f"configs[4]: cosplbl_prop prototype labeller, loader batches of {bs} {h}x{w} images, 256-d features, {c} classes, {nseg} superpixels, rho={rho}",
            "metric": "images/s through pseudo_label_generation", "unit": "images/s", "value": 1e3 / ms, "ms": ms,
+           "ms_single_image_call": ms_single, "batch": bs, "batched_labels_equal_single_image_calls": batch_equal,
            "selected_frac": round(sel, 4), "touched_frac": round(touched_frac, 4), "labelled_frac": round(float((out_lab != 255).float().mean()), 4),
            "alg_bytes": int(alg), "launches_per_image": int(launches),
            "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / ms / 1e6 / peak,
-                        "how": "algorithmic bytes of one image / CUDA-event time per image (all kernels + glue)"}}
+                        "frac_single_image_call": alg / ms_single / 1e6 / peak,
+                        "how": "algorithmic bytes of one image / CUDA-event time per image (all kernels + glue) of a batched call; "
+                               "frac_single_image_call: the same for calls with one image (no overlap between images)"}}
     if ctx.args.no_cpu_baseline:
         return out
     torch.set_num_threads(os.cpu_count() or 1)

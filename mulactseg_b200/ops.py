@@ -513,10 +513,13 @@ def _labeller_workspace(device, fch, c, h, w, nseg) -> torch.Tensor:
 
 
 def proto_labeller(feats: torch.Tensor, logits: torch.Tensor, targets: torch.Tensor, mask: torch.Tensor, spx: torch.Tensor,
-                   only_multihot: bool, threshold: str):
+                   only_multihot: bool, threshold: str, labels: Optional[torch.Tensor] = None,
+                   status: Optional[torch.Tensor] = None):
     """One image: feats (F,H,W) f32|bf16 -- or the head's LOW-RESOLUTION (F,h,w) map, interpolated inside the kernels --,
     logits (C,H,W) f32, targets (S,Ct) u8, mask (H,W) bool, spx (H,W) i32|i64
-    -> (labels (H,W) uint8, status (1,) int32 on the device).  See ``mas_proto_labeller_src_dev``."""
+    -> (labels (H,W) uint8, status (1,) int32 on the device).  See ``mas_proto_labeller_src_dev``.
+    ``labels`` / ``status``: optional preallocated outputs (status must be zero) -- the batched caller allocates them on
+    its own stream and runs the images on side streams."""
     _want(feats, "feats", (torch.float32, torch.bfloat16), 3)
     _want(logits, "inputs", torch.float32, 3)
     _want(targets, "targets", torch.uint8, 2)
@@ -531,8 +534,12 @@ def proto_labeller(feats: torch.Tensor, logits: torch.Tensor, targets: torch.Ten
         raise RuntimeError(f"feats ({fh}x{fw}) larger than the image ({h}x{w})")
     if threshold not in ("median", "min"):
         raise NotImplementedError(f"cosprop_threshold_method={threshold!r}")
-    labels = torch.empty((h, w), dtype=torch.uint8, device=feats.device)
-    status = torch.zeros(1, dtype=torch.int32, device=feats.device)
+    if labels is None:
+        labels = torch.empty((h, w), dtype=torch.uint8, device=feats.device)
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=feats.device)
+    if labels.dtype != torch.uint8 or tuple(labels.shape) != (h, w) or not labels.is_contiguous() or status.dtype != torch.int32:
+        raise RuntimeError("labels must be a contiguous (H,W) uint8 tensor and status an int32 tensor")
     ws = _labeller_workspace(feats.device, fch, c, h, w, nseg)
     with _on(feats):
         _lib.call("mas_proto_labeller_src_dev", feats.data_ptr(), _lib.MAS_F32 if feats.dtype == torch.float32 else _lib.MAS_BF16,

@@ -191,3 +191,20 @@ def test_full_size_properties():
     # idempotent / deterministic
     again = labeller.pseudo_label_generation(None, feats, logits, trg, mask, spx)
     assert torch.equal(out, again)
+
+
+def test_batched_call_runs_images_on_side_streams_and_equals_single_image_calls():
+    """A loader batch is labelled image by image on up to four side streams (one workspace per stream): same labels as
+    one call per image on the caller's stream, for more images than streams, and the result is ordered after the join."""
+    from mulactseg_b200 import labeller
+    n, c, h, w, nseg, f = 6, 8, 40, 72, 30, 16
+    feats = synth.features(n, f, h, w, seed=1, device=DEV)
+    logits = synth.logits(n, c, h, w, "normal", seed=2, device=DEV)
+    spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=3, device=DEV)
+    trg = synth.multihot_targets(n, nseg, c, seed=4, device=DEV, p_extra=0.2, p_ignore=0.0)
+    mask = synth.region_mask(spx, nseg, 0.3, seed=5)
+    for _ in range(3):
+        batch = labeller.pseudo_label_generation(None, feats, logits, trg, mask, spx)
+        for i in range(n):
+            one = labeller.pseudo_label_generation(None, feats[i:i + 1], logits[i:i + 1], trg[i:i + 1], mask[i:i + 1], spx[i:i + 1])
+            assert torch.equal(batch[i], one[0]), i
