@@ -423,6 +423,21 @@ int mas_proto_labeller_src_dev(const void* feats, int feat_dtype, int feat_chann
                                int only_multihot, int threshold_mode, uint8_t* labels, int32_t* status, void* workspace,
                                size_t workspace_bytes, void* stream);
 
+/* mas_proto_labeller_batch_dev -- mas_proto_labeller_src_dev over a loader batch, as the reference's loop calls
+ * pseudo_label_generation(labels, feats, inputs, targets, spmasks, superpixels) with batched tensors
+ * (trainer/eval_save_cosplbl_prop_includeonehot.py:121-130): feats (n_img, F, fh, fw), logits (n_img, C, H, W), targets
+ * (n_img, nseg, Ct), mask / ids / labels (n_img, H, W), status (n_img) int32 ZEROED by the caller, all contiguous.
+ * Image i runs on lane_streams[i % n_lanes] (n_lanes <= 16 caller-owned streams) with the workspace slice
+ * [lane * workspace_bytes_per_lane, ...) -- workspace_bytes_per_lane >= mas_proto_labeller_workspace_bytes(), a multiple
+ * of 256 -- forked from and joined to `stream`; n_lanes <= 1 runs the images one after the other on `stream`.  Same
+ * labels as n_img calls of mas_proto_labeller_src_dev.
+ */
+int mas_proto_labeller_batch_dev(const void* feats, int feat_dtype, int feat_channels, int feat_height, int feat_width,
+                                 const float* logits, int channels, const uint8_t* targets, int target_channels,
+                                 const uint8_t* mask, const void* ids, int ids_dtype, int n_img, int height, int width, int nseg,
+                                 int only_multihot, int threshold_mode, uint8_t* labels, int32_t* status, void* workspace,
+                                 size_t workspace_bytes_per_lane, void* const* lane_streams, int n_lanes, void* stream);
+
 /* ------------------------------------------------------------------ offline multi-hot label generation
  *
  * mas_multihot_labels_dev -- ONE image of RegionCityscapesTensor.__getitem__ (dataloader/region_cityscapes_tensor.py:33-84,

@@ -15,6 +15,8 @@ low-resolution (N,F,h,w) map, which the kernels interpolate on the fly (SURVEY.m
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib, ops
@@ -27,14 +29,14 @@ def _prep(targets, spmasks, superpixels):
     return trg, mask, spx
 
 
-_LANES = 4           # images of a batch in flight at once (side streams; one workspace per stream)
+_LANES = max(1, min(16, int(os.environ.get("MAS_LABELLER_LANES", "8"))))      # images of a batch in flight at once (side streams)
 _side_streams = {}
 
 
 def _lanes(device, n):
     """Side streams for the images of a batch.  The per-image pipeline is nine short, dependent launches (a VOC image:
     ~0.2 ms of mostly launch latency and tails), and the images are independent, so up to ``_LANES`` of them run
-    concurrently; the labels are the ones the sequential loop of the reference produces."""
+    concurrently (each on its own workspace slice); the labels are the ones the reference's sequential loop produces."""
     index = device.index if device.index is not None else torch.cuda.current_device()
     lanes = _side_streams.get(index)
     if lanes is None:
@@ -55,22 +57,8 @@ def pseudo_label_generation(labels, feats, inputs, targets, spmasks, superpixels
     # low-resolution map (interpolated inside the kernels, ``mas_proto_labeller_src_dev``)
     feats = feats.contiguous() if feats.dtype in (torch.float32, torch.bfloat16) else feats.contiguous().float()
     inputs = inputs.contiguous().float()
-    h, w = inputs.shape[2], inputs.shape[3]
-    lab = torch.empty((n, h, w), dtype=torch.uint8, device=feats.device)
-    stats = torch.zeros(n, dtype=torch.int32, device=feats.device)
-    if n > 1:
-        main = torch.cuda.current_stream(feats.device)
-        lanes = _lanes(feats.device, n)
-        for lane in lanes:
-            lane.wait_stream(main)           # inputs and the zeroed status words are ready
-        for i in range(n):
-            with torch.cuda.stream(lanes[i % len(lanes)]):
-                ops.proto_labeller(feats[i], inputs[i], trg[i], mask[i], spx[i], only_multihot, threshold, lab[i], stats[i:i + 1])
-        for lane in lanes:
-            main.wait_stream(lane)
-    else:
-        for i in range(n):
-            ops.proto_labeller(feats[i], inputs[i], trg[i], mask[i], spx[i], only_multihot, threshold, lab[i], stats[i:i + 1])
+    # one library call per loader batch: the images are dealt to side streams inside (mas_proto_labeller_batch_dev)
+    lab, stats = ops.proto_labeller_batch(feats, inputs, trg, mask, spx, only_multihot, threshold, _lanes(feats.device, n))
     out = lab.long()
     if check:
         bad = int(stats.sum())

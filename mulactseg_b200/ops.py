@@ -549,6 +549,54 @@ def proto_labeller(feats: torch.Tensor, logits: torch.Tensor, targets: torch.Ten
     return labels, status
 
 
+_batch_workspaces = {}
+
+
+def proto_labeller_batch(feats: torch.Tensor, logits: torch.Tensor, targets: torch.Tensor, mask: torch.Tensor, spx: torch.Tensor,
+                         only_multihot: bool, threshold: str, lanes):
+    """A loader batch in ONE library call (``mas_proto_labeller_batch_dev``): feats (N,F,fh,fw) f32|bf16, logits (N,C,H,W) f32,
+    targets (N,S,Ct) u8, mask (N,H,W) bool, spx (N,H,W) i32|i64, ``lanes``: side streams (torch.cuda.Stream) the images are
+    dealt to round-robin -> (labels (N,H,W) uint8, status (N,) int32 on the device)."""
+    import ctypes
+    _want(feats, "feats", (torch.float32, torch.bfloat16), 4)
+    _want(logits, "inputs", torch.float32, 4)
+    _want(targets, "targets", torch.uint8, 3)
+    _want(mask, "spmasks", (torch.bool, torch.uint8), 3)
+    _want(spx, "superpixels", (torch.int32, torch.int64), 3)
+    n, fch, fh, fw = feats.shape
+    _, c, h, w = logits.shape
+    nseg, ct = targets.shape[1], targets.shape[2]
+    if logits.shape[0] != n or targets.shape[0] != n or tuple(mask.shape) != (n, h, w) or tuple(spx.shape) != (n, h, w):
+        raise RuntimeError("feats / inputs / targets / spmasks / superpixels batch or spatial shapes differ")
+    if fh > h or fw > w:
+        raise RuntimeError(f"feats ({fh}x{fw}) larger than the image ({h}x{w})")
+    if threshold not in ("median", "min"):
+        raise NotImplementedError(f"cosprop_threshold_method={threshold!r}")
+    device = feats.device
+    labels = torch.empty((n, h, w), dtype=torch.uint8, device=device)
+    status = torch.zeros(n, dtype=torch.int32, device=device)
+    if n == 0:
+        return labels, status
+    shape = (fch, c, h, w, nseg)
+    need = _workspace_bytes.get(shape)
+    if need is None:
+        need = _workspace_bytes[shape] = int(_lib.load().mas_proto_labeller_workspace_bytes(fch, c, h, w, nseg))
+    per_lane = (need + 255) // 256 * 256
+    n_lanes = max(1, min(len(lanes), n))
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (index, torch._C._cuda_getCurrentRawStream(index))
+    ws = _batch_workspaces.get(key)
+    if ws is None or ws.numel() < per_lane * n_lanes:
+        ws = _batch_workspaces[key] = torch.empty(per_lane * n_lanes, dtype=torch.uint8, device=device)
+    handles = (ctypes.c_void_p * n_lanes)(*[s.cuda_stream for s in lanes[:n_lanes]])
+    with _on(feats):
+        _lib.call("mas_proto_labeller_batch_dev", feats.data_ptr(), _lib.MAS_F32 if feats.dtype == torch.float32 else _lib.MAS_BF16,
+                  fch, fh, fw, logits.data_ptr(), c, targets.data_ptr(), ct, mask.data_ptr(), spx.data_ptr(), _ids_dtype(spx), n, h, w,
+                  nseg, int(bool(only_multihot)), _lib.MAS_THRESHOLD_MEDIAN if threshold == "median" else _lib.MAS_THRESHOLD_MIN,
+                  labels.data_ptr(), status.data_ptr(), ws.data_ptr(), per_lane, handles, n_lanes, _stream(feats))
+    return labels, status
+
+
 # ------------------------------------------------------------------------------------------------ offline label generation
 def multihot_labels(spx: torch.Tensor, target: torch.Tensor, keep: torch.Tensor, nseg: int, num_classes: int,
                     trim_kernel_size: int = 0):
