@@ -250,13 +250,28 @@ __global__ void __launch_bounds__(256) tile_scan_kernel(const uint8_t* __restric
             const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
             const int x0 = tx * 32, x1 = min(x0 + 32, W), y0 = ty * kListRows, y1 = min(y0 + kListRows, H);
             const uint8_t* base = mask + (size_t)img * P;
-            for (int y = y0; y < y1; ++y) {
-                const uint8_t* row = base + (size_t)y * W;
-                int x = x0;
-                // 32-bit reads over the aligned middle of the 32-byte run
-                for (; x < x1 && ((reinterpret_cast<uintptr_t>(row + x)) & 3); ++x) any |= row[x] != 0;
-                for (; x + 4 <= x1; x += 4) any |= *reinterpret_cast<const uint32_t*>(row + x) != 0u;
-                for (; x < x1; ++x) any |= row[x] != 0;
+            if (x1 - x0 == 32 && y1 - y0 == kListRows && (W & 15) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0) {
+                // full tile of 16-byte aligned rows: sixteen independent 128-bit loads, OR-reduced
+                uint4 q[2 * kListRows];
+#pragma unroll
+                for (int r = 0; r < kListRows; ++r) {
+                    const uint4* row = reinterpret_cast<const uint4*>(base + (size_t)(y0 + r) * W + x0);
+                    q[2 * r] = __ldg(row);
+                    q[2 * r + 1] = __ldg(row + 1);
+                }
+                uint32_t acc = 0u;
+#pragma unroll
+                for (int k = 0; k < 2 * kListRows; ++k) acc |= q[k].x | q[k].y | q[k].z | q[k].w;
+                any = acc != 0u;
+            } else {
+                for (int y = y0; y < y1; ++y) {
+                    const uint8_t* row = base + (size_t)y * W;
+                    int x = x0;
+                    // 32-bit reads over the aligned middle of the 32-byte run
+                    for (; x < x1 && ((reinterpret_cast<uintptr_t>(row + x)) & 3); ++x) any |= row[x] != 0;
+                    for (; x + 4 <= x1; x += 4) any |= *reinterpret_cast<const uint32_t*>(row + x) != 0u;
+                    for (; x < x1; ++x) any |= row[x] != 0;
+                }
             }
         }
         const uint32_t word = __ballot_sync(0xffffffffu, any);
