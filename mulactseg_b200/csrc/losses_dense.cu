@@ -440,6 +440,12 @@ multihot_dense_bwd_kernel(const __grid_constant__ DenseMaps maps, const LossPara
             live[j] = grp[j] || (do_choice && bits != 0u);            // does any gradient reach this pixel?
             any_live |= live[j];
         }
+        // Refill the stage whose gradient row left one iteration ago -- here, not after this row's store: the id / candidate
+        // gathers above gave that store time to drain, and the next row's loads now overlap this row's arithmetic
+        if (lane == 0 && issued < r1) {
+            store_wait_read<0>();
+            issue(s == 0 ? stages - 1 : s - 1);
+        }
         if (!__any_sync(kFull, any_live)) {
             float z[kPx];
 #pragma unroll
@@ -581,10 +587,6 @@ multihot_dense_bwd_kernel(const __grid_constant__ DenseMaps maps, const LossPara
         if (lane == 0) {
             store_4d(&maps.grad, smem_u32(st), at.strip * kStripPx, at.y, 0, at.img);
             store_commit();
-            if (issued < r1) {
-                store_wait_read<1>();      // the store issued one row ago has drained the stage that is refilled now
-                issue(s == 0 ? stages - 1 : s - 1);
-            }
         }
         if (++s == stages) { s = 0; parity ^= 1u; }
         at.advance(d.strips, p.H);
