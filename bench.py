@@ -140,13 +140,29 @@ def committed_traffic(name: str):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 25 ms.  The sampler is started well before the timed region
-    (nvidia-smi takes a moment to come up); ``stop(t0, t1)`` keeps the samples whose timestamps fall inside it."""
+    """SM clock and throttle reasons DURING the timed region: an NVML polling thread (one sample every ~5 ms; the timed
+    region of a default run is ~0.1-0.2 s), with the ``nvidia-smi -lms`` loop of the profiling recipe as the fallback when
+    the NVML binding is missing.  Started ahead of the timed region; ``stop(t0, t1)`` keeps the samples inside it."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    INTERVAL_MS = 5
 
     def __init__(self, index: int):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.alive = [], None, None, True
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(index), "-lms", "25"], stdout=subprocess.PIPE, text=True)
@@ -155,11 +171,36 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))
+        bits = [(name, getattr(n, new, None) or getattr(n, old, 0)) for name, new, old in names]
+        query = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while self.alive:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(query(self.handle))
+                self.rows.append((time.time(), mhz, [name for name, bit in bits if bit and (mask & bit)]))
+            except Exception:
+                pass
+            time.sleep(self.INTERVAL_MS / 1e3)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [p.strip() for p in line.split(",")]))
 
     def stop(self, t0: float, t1: float):
+        if self.nvml is not None:
+            self.alive = False
+            self.thread.join(timeout=2)
+            inside = [r for r in self.rows if t0 <= r[0] <= t1]
+            sm = [r[1] for r in inside]
+            reasons = sorted({name for r in inside for name in r[2]})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": reasons, "samples": len(sm), "interval_ms": self.INTERVAL_MS, "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.1)
@@ -182,7 +223,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "interval_ms": 25}
+                "reasons": sorted(reasons), "samples": len(sm), "interval_ms": 25, "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU port (oracle)
@@ -735,7 +776,8 @@ def run_losses(ctx: Ctx, rho: float, steps: int):
                         "how": "algorithmic bytes of the whole step / CUDA-event time of the whole step through the nn.Module API "
                                "(kernels + autograd + the trainer's scalar arithmetic; host-bound at small rho)",
                         "frac_kernels_only": alg / ms_kernels / 1e6 / peak,
-                        "kernels_only": "mas_stage1_loss_fwd_dev + mas_stage1_loss_bwd_dev back to back (8 kernels), CUDA events"}}
+                        "kernels_only": "mas_stage1_loss_fwd_dev + mas_stage1_loss_bwd_dev back to back, CUDA events (both kernel sets -- "
+                                        "TMA strip walk for densely selected batches, active-tile list walk otherwise -- are launched; the device picks)"}}
     if ctx.args.no_cpu_baseline:
         return out
     # CPU port on a bounded sample (the first 2 crops) -- and the parity of the GPU step on exactly those crops

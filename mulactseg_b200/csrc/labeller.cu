@@ -43,6 +43,7 @@ struct LabelParams {
     int F, C, H, W, S, P;
     int threshold_min;      // 0: lower median, 1: min
     int only_multihot;
+    int overlapped;      // other images of the batch run concurrently on other streams (mas_proto_labeller_batch_dev)
     int32_t* status;
     const uint32_t* info;               // (S)
     const unsigned long long* gmax;     // (S, C)
@@ -866,9 +867,11 @@ int run_labeller(const LabelParams& p, const Workspace& w, cudaStream_t st) {
     {
         // two traversals, same labels: spatial tiles (fewer DRAM bytes, more parallelism on small images; measured on a
         // 375 x 500 image: 0.256 -> 0.223 ms per image) or one CTA per superpixel slice (less per-CTA overhead; 1024 x 2048:
-        // 0.57 vs 0.63 ms).  MAS_LABELLER_TILE = 0 / 1 forces one.
+        // 0.57 vs 0.63 ms).  When the images of a batch overlap on several streams the extra parallelism of the tiles buys
+        // nothing and their per-tile overhead costs (375 x 500, 8 lanes: 0.076 vs 0.092 ms per image): superpixel walk.
+        // MAS_LABELLER_TILE = 0 / 1 forces one.
         const char* v = getenv("MAS_LABELLER_TILE");
-        const bool tile = (v && (v[0] == '0' || v[0] == '1')) ? v[0] == '1' : p.P <= (1 << 19);
+        const bool tile = (v && (v[0] == '0' || v[0] == '1')) ? v[0] == '1' : (p.P <= (1 << 19) && !p.overlapped);
         if (tile) {
             const dim3 grid_t((unsigned)((p.W + kTileW - 1) / kTileW), (unsigned)((p.H + kTileH - 1) / kTileH));
             proto_propagate_tile_kernel<FT, LOWRES, IdT><<<grid_t, kAssignThreads, smem + 2 * (size_t)p.words * sizeof(uint32_t), st>>>(p);
@@ -915,7 +918,7 @@ namespace {
 int proto_labeller_impl(const char* what, const void* feats, int feat_dtype, int feat_channels, int feat_height, int feat_width,
                         const float* logits, int channels, const uint8_t* targets, int target_channels, const uint8_t* mask,
                         const void* ids, int ids_dtype, int height, int width, int nseg, int only_multihot, int threshold_mode,
-                        uint8_t* labels, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+                        uint8_t* labels, int32_t* status, void* workspace, size_t workspace_bytes, void* stream, bool overlapped = false) {
     MAS_REQUIRE(feats && logits && targets && mask && ids && labels && status && workspace, MAS_E_BADARG, "%s: null pointer", what);
     MAS_REQUIRE(feat_channels > 0 && height > 0 && width > 0 && nseg > 0, MAS_E_BADARG, "%s: bad shape", what);
     MAS_REQUIRE(feat_dtype == MAS_F32 || feat_dtype == MAS_BF16, MAS_E_BADARG, "%s: bad feature dtype", what);
@@ -961,6 +964,7 @@ int proto_labeller_impl(const char* what, const void* feats, int feat_dtype, int
     p.own_sim = w.own_sim; p.own_cls = w.own_cls; p.thr = w.thr; p.adj = w.adj; p.svalid = w.svalid; p.touched = w.touched;
     p.words = (nseg + 31) / 32;
     p.labels = labels;
+    p.overlapped = overlapped ? 1 : 0;
     const bool i64 = ids_dtype == MAS_I64, bf16 = feat_dtype == MAS_BF16;
 #define MAS_RUN(IdT)                                                                                                   \
     (bf16 ? (lowres ? run_labeller<IdT, __nv_bfloat16, true>(p, w, st) : run_labeller<IdT, __nv_bfloat16, false>(p, w, st)) \
@@ -1030,7 +1034,8 @@ extern "C" int mas_proto_labeller_batch_dev(const void* feats, int feat_dtype, i
         return proto_labeller_impl("proto_labeller_batch", (const char*)feats + (size_t)i * feat_img, feat_dtype, feat_channels, feat_height,
                                    feat_width, logits + (size_t)i * channels * P, channels, targets + (size_t)i * nseg * target_channels,
                                    target_channels, mask + (size_t)i * P, (const char*)ids + (size_t)i * id_img, ids_dtype, height, width, nseg,
-                                   only_multihot, threshold_mode, labels + (size_t)i * P, status + i, ws, workspace_bytes_per_lane, st);
+                                   only_multihot, threshold_mode, labels + (size_t)i * P, status + i, ws, workspace_bytes_per_lane, st,
+                                   std::min(n_lanes, n_img) > 1);
     };
     const int lanes = std::min(n_lanes, n_img);
     if (lanes <= 1) {      // nothing to overlap: everything on the caller's stream (or the single lane's)

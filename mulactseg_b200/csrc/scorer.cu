@@ -213,17 +213,28 @@ bvsb_stats_tma_kernel(const __grid_constant__ TmaMaps maps, const StatsParams p)
                 const int4 q = *reinterpret_cast<const int4*>(st + (size_t)C * plane_bytes + lane * 16);
                 id[0] = q.x; id[1] = q.y; id[2] = q.z; id[3] = q.w;
             }
-            float v[CMAX][4];
+            if (sizeof(T) == 2) {
+                // bf16: the planes stay packed (two pixels per register) for the top-2 scan, see Walker::row_bf16
+                uint2 q[CMAX];
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c) {
-                if (EXACT || c < C) {
-                    VecLoad<T, 4>::shared(reinterpret_cast<const T*>(st + (size_t)c * plane_bytes) + lane * 4, v[c]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) v[c][j] = -INFINITY;
+                for (int c = 0; c < CMAX; ++c) {
+                    q[c] = (EXACT || c < C) ? *reinterpret_cast<const uint2*>(st + (size_t)c * plane_bytes + lane * 8)
+                                            : make_uint2(0xff80ff80u, 0xff80ff80u);
                 }
+                w.row_bf16(q, id);
+            } else {
+                float v[CMAX][4];
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c) {
+                    if (EXACT || c < C) {
+                        VecLoad<T, 4>::shared(reinterpret_cast<const T*>(st + (size_t)c * plane_bytes) + lane * 4, v[c]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[c][j] = -INFINITY;
+                    }
+                }
+                w.row(v, id);
             }
-            w.row(v, id);
         }
         __syncwarp();   // every lane is done with stage s (its loads fed the column updates above)
         if (lane == 0 && issued < r1) {

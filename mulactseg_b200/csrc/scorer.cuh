@@ -190,7 +190,11 @@ struct Walker {
                 pacc[c] = t;
             }
         }
-        // ---- then the segmented accumulation
+        accumulate(bvsb, top1, id);
+    }
+
+    // the segmented accumulation of one row: bvsb[j] / top1[j] of the VEC pixels with ids id[j]
+    __device__ __forceinline__ void accumulate(const float (&bvsb)[VEC], const int (&top1)[VEC], const int (&id)[VEC]) {
         // does this row still touch the current superpixel?  if not, move on to the row's first id
         // ids outside [0, S) (crop padding, -1, garbage) become -2: never equal to `cur` (>= -1), never accumulated
         int sid[VEC];
@@ -217,6 +221,70 @@ struct Walker {
                 atomicAdd(cls_cnt + r, 1);
             }
         }
+    }
+
+    // bf16 rows (VEC == 4; q[c] = the lane's four bf16 logits of plane c as two packed pairs): the top-2 / arg-max scan
+    // runs on the PACKED pairs -- min / max / compare on bf16x2 are exact, so m1, m2 and the arg-max (first index on ties,
+    // strict >) equal the fp32 scan of the widened values at 3 instead of 5 instructions per (class, pixel); only the
+    // softmax sums widen the values.
+    __device__ __forceinline__ void row_bf16(const uint2 (&q)[CMAX], const int (&id)[VEC]) {
+        static_assert(VEC == 4, "packed bf16 rows are 4 pixels wide");
+        uint32_t m1p[2] = {q[0].x, q[0].y}, m2p[2] = {0xff80ff80u, 0xff80ff80u};      // -inf pairs
+        int top1[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) top1[j] = 0;
+#pragma unroll
+        for (int c = 1; c < CMAX; ++c) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t x = h == 0 ? q[c].x : q[c].y;
+                uint32_t t;
+                asm("{\n\t"
+                    ".reg .pred lo, hi;\n\t"
+                    "setp.gt.bf16x2 lo|hi, %3, %4;\n\t"
+                    "selp.s32 %0, %5, %0, lo;\n\t"
+                    "selp.s32 %1, %5, %1, hi;\n\t"
+                    "min.bf16x2 %2, %4, %3;\n\t"
+                    "}"
+                    : "+r"(top1[2 * h]), "+r"(top1[2 * h + 1]), "=r"(t)
+                    : "r"(x), "r"(m1p[h]), "r"(c));
+                asm("max.bf16x2 %0, %0, %1;" : "+r"(m2p[h]) : "r"(t));
+                asm("max.bf16x2 %0, %0, %1;" : "+r"(m1p[h]) : "r"(x));
+            }
+        }
+        float m1[VEC], m2[VEC], bvsb[VEC];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            m1[2 * h] = __uint_as_float(m1p[h] << 16); m1[2 * h + 1] = __uint_as_float(m1p[h] & 0xffff0000u);
+            m2[2 * h] = __uint_as_float(m2p[h] << 16); m2[2 * h + 1] = __uint_as_float(m2p[h] & 0xffff0000u);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) bvsb[j] = mas::ex2_approx((m2[j] - m1[j]) * scale) + 1e-8f;
+        if (NEED_PROB) {
+            float shift[VEC], den_a[VEC], den_b[VEC], e[CMAX][VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) { shift[j] = -m1[j] * scale; den_a[j] = 0.f; den_b[j] = 0.f; }
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) {
+                const float x[VEC] = {__uint_as_float(q[c].x << 16), __uint_as_float(q[c].x & 0xffff0000u),
+                                      __uint_as_float(q[c].y << 16), __uint_as_float(q[c].y & 0xffff0000u)};
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    e[c][j] = mas::ex2_approx(fmaf(x[j], scale, shift[j]));   // padded planes hold -inf -> 0
+                    if (c & 1) den_b[j] += e[c][j]; else den_a[j] += e[c][j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) den_a[j] = mas::rcp_approx(den_a[j] + den_b[j]);
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) {
+                float t = pacc[c];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) t = fmaf(e[c][j], den_a[j], t);
+                pacc[c] = t;
+            }
+        }
+        accumulate(bvsb, top1, id);
     }
 };
 
