@@ -305,9 +305,14 @@ int mas_multihot_loss_bwd_dev(const float* logits, const void* ids, int ids_dtyp
  * *_tiles_dev twins of the two passes take that list:
  *   forward : only the active tiles are visited, dealt round-robin BY RANK to the warps (balanced whatever the layout of
  *             the labelled regions; deterministic -- no atomic queue);
- *   backward: when fewer than 35 % of the tiles are active the dense gradient is zeroed by one linear sweep and only the
- *             active tiles are computed on top; otherwise the tile walk of mas_multihot_loss_bwd_dev runs unchanged.
- * Results are those of the plain entry points (tiles == NULL falls back to them).
+ *   backward: a sparsely selected batch gets its dense gradient zeroed by one linear sweep and only the active tiles
+ *             computed on top;
+ *   both    : when at least 40 % of the tiles are active and the shape allows (W % 16 == 0, 16-byte aligned bases, fast
+ *             softmax) the batch is taken by the DENSE kernels instead (csrc/losses_dense.cu: TMA-staged 64-pixel strip
+ *             rows, the gradient leaves by TMA store).  The choice is made ON THE DEVICE from the active-tile count: both
+ *             kernel sets are launched and one returns at once, so no call ever synchronises.  Other shapes: below 35 %
+ *             the list walk, otherwise the tile walk of the plain entry points.
+ * Results are those of the plain entry points (tiles == NULL falls back to them) up to the order of the fp32 bucket sums.
  */
 size_t mas_multihot_tiles_workspace_bytes(int n_img, int height, int width);
 int mas_multihot_tiles_dev(const uint8_t* mask, int n_img, int height, int width, void* tiles, size_t tiles_bytes, void* stream);
