@@ -5,19 +5,19 @@
 // pixel per thread and C' strided planes per row with predicated 32-bit loads -- right when a few percent of the pixels
 // are labelled (it never touches the logits of unselected pixels), but issue-bound at ~30 instructions per (class, pixel)
 // once most pixels are selected (0.5 of the HBM peak at rho = 1).  Here, like the acquisition scorer (scorer.cu):
-//   * the unit of work is a STRIP ROW of 128 pixels (4 per lane); strip rows are linearised (image, strip, y) and cut
+//   * the unit of work is a STRIP ROW of 64 pixels (2 per lane; 16 warps per SM); strip rows are linearised (image, strip, y) and cut
 //     into one contiguous range per warp of a single-wave persistent grid, so a lane walks DOWN its four columns;
 //   * every warp runs its own ring of shared-memory stages; lane 0 issues one cp.async.bulk.tensor box
-//     {128 px, 1 row, C' planes} for the logits plus one each for the ids and the mask bytes of the row, completion on a
-//     per-stage mbarrier; the planes are then read with 128-bit shared-memory loads at constant offsets (no per-plane
+//     {64 px, 1 row, C' planes} for the logits plus one each for the ids and the mask bytes of the row, completion on a
+//     per-stage mbarrier; the planes are then read with vector shared-memory loads at constant offsets (no per-plane
 //     address arithmetic, no predicated global loads);
-//   * forward: the running maxima of the lane's current superpixel live in a private shared-memory column indexed by the
-//     RANK of the class inside the superpixel's candidate set (3 slots; further candidates and boundary straddlers go to
-//     global atomicMax directly);
-//   * backward: the gradient of the row overwrites the logits in the stage and leaves with ONE TMA store (3-stage ring:
-//     loading / computing / draining), so the dense gradient is written as full lines without 20 address computations
-//     per row either; the arg-max ownership words of a pixel's first three candidates are gathered before the softmax
-//     is computed (one latency, not one per candidate).
+//   * forward: every pixel COLUMN of a lane keeps the running maxima of the superpixel it is walking through as packed
+//     64-bit keys in registers, indexed by the RANK of the class inside the superpixel's candidate set (3 slots; further
+//     candidates go to global atomicMax directly), flushed with atomicMax when the column enters another superpixel;
+//   * backward: the gradient of the row overwrites the logits in the stage and leaves with ONE TMA store (2-stage ring,
+//     the drained stage refilled early in the next iteration), so the dense gradient is written as full lines without
+//     20 address computations per row either; the arg-max ownership words of a pixel's first three candidates are
+//     gathered before the softmax is computed (one latency, not one per candidate).
 // Out-of-range boxes are zero-filled on load (mask 0 = unselected) and clipped on store, so ragged right edges need no
 // special case.  Requirements: W % 16 == 0 (the mask rows are the narrowest TMA source) and 16-byte aligned bases;
 // anything else stays on the tile walk.
@@ -215,25 +215,33 @@ multihot_dense_fwd_kernel(const __grid_constant__ DenseMaps maps, const LossPara
             for (int s = 0; s < stages && issued < r1; ++s) issue(s);
         }
 
-        // running maxima of the lane's current superpixel: one packed (P bits, ~pixel) key per RANK of the class inside
-        // the superpixel's candidate set, held in registers (the rank is a compile-time index below)
-        int cur = -1;
-        uint32_t cur_bits = 0u;
-        int cur_base = 0;
-        unsigned long long best[kPrivRanks];
+        // running maxima of the superpixel each of the lane's pixel COLUMNS is walking through: one packed (P bits, ~pixel) key
+        // per RANK of the class inside the superpixel's candidate set, held in registers (column and rank are compile-time
+        // indices below); no pixel of a row needs a global atomic, only a column that enters another superpixel flushes
+        int cur[kPx], cur_base[kPx];
+        uint32_t cur_bits[kPx];
+        unsigned long long best[kPx][kPrivRanks];
 #pragma unroll
-        for (int k = 0; k < kPrivRanks; ++k) best[k] = 0ull;
+        for (int j = 0; j < kPx; ++j) {
+            cur[j] = -1; cur_base[j] = 0; cur_bits[j] = 0u;
+#pragma unroll
+            for (int k = 0; k < kPrivRanks; ++k) best[j][k] = 0ull;
+        }
         auto flush = [&]() {
-            if (cur < 0) return;
-            uint32_t b = cur_bits;
 #pragma unroll
-            for (int k = 0; k < kPrivRanks; ++k) {
-                const int c = b ? __ffs(b) - 1 : 0;
-                b &= b - 1u;
-                if (best[k] != 0ull) atomicMax(p.gmax + cur_base + c, best[k]);
-                best[k] = 0ull;
+            for (int j = 0; j < kPx; ++j) {
+                if (cur[j] >= 0) {
+                    uint32_t b = cur_bits[j];
+#pragma unroll
+                    for (int k = 0; k < kPrivRanks; ++k) {
+                        const int c = b ? __ffs(b) - 1 : 0;
+                        b &= b - 1u;
+                        if (best[j][k] != 0ull) atomicMax(p.gmax + cur_base[j] + c, best[j][k]);
+                        best[j][k] = 0ull;
+                    }
+                    cur[j] = -1;
+                }
             }
-            cur = -1;
         };
 
         int s = 0;
@@ -255,33 +263,36 @@ multihot_dense_fwd_kernel(const __grid_constant__ DenseMaps maps, const LossPara
                 row_logits<CMAX, EXACT>(sx, C, v);
                 row_softmax<CMAX, false>(v, p.scale, shift, inv);
 
-                // which superpixel do the private maxima serve?  (a pixel counts for the group loss when its region does)
+                // a pixel counts for the group loss when its region does; a column that left its superpixel flushes first
                 bool grp[kPx];
-                bool touches = false;
 #pragma unroll
                 for (int j = 0; j < kPx; ++j) {
                     grp[j] = do_group && (inf[j] & kGroupBit) && (inf[j] & ~kGroupBit) != 0u;      // sid >= 0 follows (inf != 0)
-                    touches |= grp[j] && sid[j] == cur;
-                }
-                if (!touches) {
-                    flush();
+                    if (grp[j] && sid[j] != cur[j]) {
+                        if (cur[j] >= 0) {
+                            uint32_t b = cur_bits[j];
 #pragma unroll
-                    for (int j = kPx - 1; j >= 0; --j) {
-                        if (grp[j]) { cur = sid[j]; cur_bits = inf[j] & ~kGroupBit; }
+                            for (int k = 0; k < kPrivRanks; ++k) {
+                                const int c = b ? __ffs(b) - 1 : 0;
+                                b &= b - 1u;
+                                if (best[j][k] != 0ull) atomicMax(p.gmax + cur_base[j] + c, best[j][k]);
+                                best[j][k] = 0ull;
+                            }
+                        }
+                        cur[j] = sid[j];
+                        cur_bits[j] = inf[j] & ~kGroupBit;
+                        cur_base[j] = (img_row + sid[j]) * C;
                     }
-                    if (cur >= 0) cur_base = (img_row + cur) * C;
                 }
                 const uint32_t pix0 = (uint32_t)at.y * (uint32_t)p.W + (uint32_t)(at.strip * kStripPx + lane * kPx);
                 // candidate classes rank by rank, the four pixels side by side (straight-line code: four independent
                 // dependency chains per rank instead of one chain per pixel)
                 uint32_t rest[kPx];
                 float pos[kPx];
-                bool mine[kPx];
 #pragma unroll
                 for (int j = 0; j < kPx; ++j) {
                     rest[j] = inf[j] & ~kGroupBit;
                     pos[j] = 0.f;
-                    mine[j] = grp[j] && sid[j] == cur;
                 }
 #pragma unroll
                 for (int k = 0; k < kPrivRanks; ++k) {
@@ -293,8 +304,7 @@ multihot_dense_fwd_kernel(const __grid_constant__ DenseMaps maps, const LossPara
                         const float pc = mas::ex2_approx(fmaf(sx[c * kStripPx + j], p.scale, shift[j])) * inv[j];
                         pos[j] += has ? pc : 0.f;
                         const unsigned long long key = ((unsigned long long)__float_as_uint(pc) << 32) | (unsigned long long)(~(pix0 + j));
-                        if (has && mine[j]) best[k] = key > best[k] ? key : best[k];
-                        if (has && grp[j] && !mine[j]) atomicMax(p.gmax + ((img_row + sid[j]) * C + c), key);
+                        if (has && grp[j]) best[j][k] = key > best[j][k] ? key : best[j][k];
                     }
                 }
                 uint32_t rest_any = 0u;
