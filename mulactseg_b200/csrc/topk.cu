@@ -210,7 +210,7 @@ __global__ void merge_counts_kernel(unsigned long long* gathered, int world, lon
 // cost exceed the budget (strict '>', dataloader/region_active_dataset.py:56-66).  One CTA: gather the cost of every
 // ranked region, block-wide inclusive scan with a running carry, first index over the budget.
 constexpr int kCutThreads = 1024;
-constexpr int kCutPer = 4;
+constexpr int kCutPer = 16;        // 16 independent key loads + cost gathers in flight per thread and pass (4: 49 us per round, latency-bound)
 
 __global__ void __launch_bounds__(kCutThreads) prefix_cut_kernel(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ count,
                                                                  const uint8_t* __restrict__ cost_by_tie, long long n_cost,
