@@ -183,7 +183,12 @@ class ClockSampler:
             try:
                 mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
                 mask = int(query(self.handle))
-                self.rows.append((time.time(), mhz, [name for name, bit in bits if bit and (mask & bit)]))
+                try:
+                    watts = n.nvmlDeviceGetPowerUsage(self.handle) / 1e3
+                    mem = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_MEM))
+                except Exception:
+                    watts, mem = None, None
+                self.rows.append((time.time(), mhz, [name for name, bit in bits if bit and (mask & bit)], watts, mem))
             except Exception:
                 pass
             time.sleep(self.INTERVAL_MS / 1e3)
@@ -199,8 +204,21 @@ class ClockSampler:
             inside = [r for r in self.rows if t0 <= r[0] <= t1]
             sm = [r[1] for r in inside]
             reasons = sorted({name for r in inside for name in r[2]})
-            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": self.max_mhz,
-                    "reasons": reasons, "samples": len(sm), "interval_ms": self.INTERVAL_MS, "source": "nvml"}
+            watts = [r[3] for r in inside if r[3] is not None]
+            mem = [r[4] for r in inside if r[4] is not None]
+            out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                   "reasons": reasons, "samples": len(sm), "interval_ms": self.INTERVAL_MS, "source": "nvml"}
+            if watts:
+                out["power_w"] = {"median": float(np.median(watts)), "max": max(watts)}
+                try:
+                    out["power_w"]["limit"] = self.nvml.nvmlDeviceGetEnforcedPowerLimit(self.handle) / 1e3
+                except Exception:
+                    pass
+            if mem:
+                out["mem_mhz"] = {"median": float(np.median(mem)), "min": min(mem)}
+            # the samples in order, for runs that want to see WHEN a clock or the power changed
+            out["trace"] = [[round((r[0] - t0) * 1e3, 1), r[1], r[3]] for r in inside][:64]
+            return out
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.1)
