@@ -159,16 +159,22 @@ bvsb_stats_tma_kernel(const __grid_constant__ TmaMaps maps, const StatsParams p)
     const int C = EXACT ? CMAX : p.C;
     const int stages = p.stages;
     const uint32_t plane_bytes = kTmaStripPx * sizeof(T);
-    const uint32_t stage_bytes = (uint32_t)C * plane_bytes + kTmaStripPx * sizeof(int32_t);
+    constexpr uint32_t kIdBytes = kTmaStripPx * sizeof(int32_t);
+    // p.split_ids: the id rows do not ride in the logits stages but in ONE buffer per warp with its own barrier (it is
+    // read into registers at the top of a row and refilled at once) -- 512 bytes per warp and stage less, which is what
+    // lets an eighth warp fit at C' = 21 / 22 fp32
+    const bool split = p.split_ids != 0;
+    const uint32_t stage_bytes = (uint32_t)C * plane_bytes + (split ? 0u : kIdBytes);
     unsigned char* my_stages = smem + (size_t)warp * stages * stage_bytes;
-    uint2* columns = reinterpret_cast<uint2*>(smem + (size_t)warps * stages * stage_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(columns + (size_t)C * threads) + warp * stages;
+    unsigned char* my_ids = smem + (size_t)warps * stages * stage_bytes + (size_t)warp * kIdBytes;      // split mode only
+    uint2* columns = reinterpret_cast<uint2*>(smem + (size_t)warps * stages * stage_bytes + (split ? (size_t)warps * kIdBytes : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(columns + (size_t)C * threads) + warp * (stages + 1);      // [stages] logits, then ids
 
     Walker<CMAX, EXACT, 4, NEED_PROB> w;
     w.init(columns + tid, threads, p);
 
     if (lane == 0) {
-        for (int s = 0; s < stages; ++s) mbar_init(smem_u32(bars + s), 1u);
+        for (int s = 0; s <= stages; ++s) mbar_init(smem_u32(bars + s), 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -192,11 +198,24 @@ bvsb_stats_tma_kernel(const __grid_constant__ TmaMaps maps, const StatsParams p)
         const int local = ahead.img - p.seg_first[ahead_seg];
         mbar_expect_tx(bar, stage_bytes);
         tma_load_4d(dst, &maps.logits[ahead_seg], bar, ahead.strip * kTmaStripPx, ahead.y, 0, local, policy);
-        tma_load_3d(dst + (uint32_t)C * plane_bytes, &maps.ids[ahead_seg], bar, ahead.strip * kTmaStripPx, ahead.y, local, policy);
+        if (!split) tma_load_3d(dst + (uint32_t)C * plane_bytes, &maps.ids[ahead_seg], bar, ahead.strip * kTmaStripPx, ahead.y, local, policy);
         if (ahead.advance(p.strips, p.H) == 2 && ahead_seg + 1 < p.n_seg && ahead.img >= p.seg_first[ahead_seg + 1]) ++ahead_seg;
         ++issued;
     };
+    // split mode: the id row of the next strip row -> the warp's single id buffer
+    mas::Cursor ahead_id = at;
+    long long issued_id = r0;
+    int ahead_id_seg = ahead_seg;
+    auto issue_ids = [&]() {  // lane 0 only
+        const uint32_t bar = smem_u32(bars + stages);
+        mbar_expect_tx(bar, kIdBytes);
+        tma_load_3d(smem_u32(my_ids), &maps.ids[ahead_id_seg], bar, ahead_id.strip * kTmaStripPx, ahead_id.y,
+                    ahead_id.img - p.seg_first[ahead_id_seg], policy);
+        if (ahead_id.advance(p.strips, p.H) == 2 && ahead_id_seg + 1 < p.n_seg && ahead_id.img >= p.seg_first[ahead_id_seg + 1]) ++ahead_id_seg;
+        ++issued_id;
+    };
     if (lane == 0) {
+        if (split) issue_ids();
         for (int s = 0; s < stages && issued < r1; ++s) issue(s);
     }
 
@@ -204,12 +223,25 @@ bvsb_stats_tma_kernel(const __grid_constant__ TmaMaps maps, const StatsParams p)
     bool active = (at.strip * kTmaStripPx + lane * 4) < p.W;
     int s = 0;
     uint32_t parity = 0;
+    uint32_t parity_id = 0;
     for (long long r = r0; r < r1; ++r) {
+        int id[4];
+        if (split) {
+            // ids first: into registers, and the buffer is refilled with the next row's ids while this row is computed
+            mbar_wait(smem_u32(bars + stages), parity_id);
+            parity_id ^= 1u;
+            const int4 q = *reinterpret_cast<const int4*>(my_ids + lane * 16);
+            id[0] = q.x; id[1] = q.y; id[2] = q.z; id[3] = q.w;
+            __syncwarp();
+            if (lane == 0 && issued_id < r1) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_ids();
+            }
+        }
         mbar_wait(smem_u32(bars + s), parity);
         if (active) {
             const unsigned char* st = my_stages + (size_t)s * stage_bytes;
-            int id[4];
-            {
+            if (!split) {
                 const int4 q = *reinterpret_cast<const int4*>(st + (size_t)C * plane_bytes + lane * 16);
                 id[0] = q.x; id[1] = q.y; id[2] = q.z; id[3] = q.w;
             }
@@ -320,7 +352,7 @@ cudaError_t launch_tma(StatsParams p, cudaStream_t stream, bool* unsupported) {
     EncodeTiledFn encode = encode_tiled();
     if (!encode) return cudaSuccess;
     const size_t elt = sizeof(T);
-    const uint32_t stage_bytes = (uint32_t)p.C * kTmaStripPx * elt + kTmaStripPx * 4;
+    uint32_t stage_bytes = (uint32_t)p.C * kTmaStripPx * elt + kTmaStripPx * 4;
     const size_t col_bytes_per_warp = (size_t)p.C * 32 * sizeof(uint2);
     const int dev = mas::current_device();
     int max_smem = 0;
@@ -329,8 +361,18 @@ cudaError_t launch_tma(StatsParams p, cudaStream_t stream, bool* unsupported) {
     int warps = env_int("MAS_SCORER_WARPS", 0);
     if (stages <= 0) stages = (elt == 2) ? 4 : 2;
     stages = std::min(std::max(stages, 2), 8);
-    const size_t per_warp = (size_t)stages * stage_bytes + col_bytes_per_warp + (size_t)stages * 8;
-    const int fit = (int)(((size_t)max_smem - 128) / per_warp);
+    size_t per_warp = (size_t)stages * stage_bytes + col_bytes_per_warp + (size_t)(stages + 1) * 8;
+    int fit = (int)(((size_t)max_smem - 128) / per_warp);
+    p.split_ids = 0;
+    if (fit < kTmaMaxWarps) {
+        // one id buffer per warp instead of one per stage: does that buy a warp?  (C' = 21 / 22 fp32: 7 -> 8 warps)
+        const uint32_t split_stage = (uint32_t)p.C * kTmaStripPx * elt;
+        const size_t split_per_warp = (size_t)stages * split_stage + kTmaStripPx * 4 + col_bytes_per_warp + (size_t)(stages + 1) * 8;
+        const int split_fit = (int)(((size_t)max_smem - 128) / split_per_warp);
+        if (split_fit > fit && env_int("MAS_SCORER_SPLIT_IDS", 1) != 0) {
+            p.split_ids = 1; stage_bytes = split_stage; per_warp = split_per_warp; fit = split_fit;
+        }
+    }
     if (warps <= 0) {
         // default: launches of up to ~1 GB run as small CTAs (2 warps, several per SM) so that the CTAs of the next launch
         // on the other lane move in warp-pair by warp-pair as this one drains (+4-5 % at 4 Cityscapes images per launch);
@@ -478,7 +520,7 @@ extern "C" int mas_bvsb_segment_stats_multi_dev(int n_segments, const void* cons
 
     p.C = channels; p.H = height; p.W = width; p.S = nseg;
     p.scale = 1.4426950408889634f / temperature;
-    p.strips = 0; p.total_rows = 0; p.stages = 0;
+    p.strips = 0; p.total_rows = 0; p.stages = 0; p.split_ids = 0;
     p.cls_sum = cls_sum; p.cls_cnt = cls_cnt; p.prob_sum = prob_sum;
     p.h_in = 0; p.w_in = 0; p.ry = 1.f; p.rx = 1.f;
 
@@ -526,7 +568,7 @@ extern "C" int mas_bvsb_segment_stats_lowres_dev(const void* logits, int logits_
     p.seg_first[0] = 0;
     p.C = channels; p.H = height; p.W = width; p.S = nseg;
     p.scale = 1.4426950408889634f / temperature;
-    p.strips = 0; p.total_rows = 0; p.stages = 0;
+    p.strips = 0; p.total_rows = 0; p.stages = 0; p.split_ids = 0;
     p.cls_sum = cls_sum; p.cls_cnt = cls_cnt; p.prob_sum = prob_sum;
     p.h_in = height_in; p.w_in = width_in;
     // torch's area_pixel_compute_scale<float>(input, output, align_corners=false, no scale factor): (float)input / output

@@ -26,6 +26,7 @@ struct StatsParams {
     int strips;              // column strips per image
     long long total_rows;    // n_img * strips * H strip rows
     int stages;              // TMA path: ring depth per warp
+    int split_ids;           // TMA path: the id rows use one buffer per warp with its own barrier instead of riding in the stages
     float* cls_sum;
     int32_t* cls_cnt;
     double* prob_sum;
