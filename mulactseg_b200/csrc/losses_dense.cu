@@ -5,8 +5,8 @@
 // pixel per thread and C' strided planes per row with predicated 32-bit loads -- right when a few percent of the pixels
 // are labelled (it never touches the logits of unselected pixels), but issue-bound at ~30 instructions per (class, pixel)
 // once most pixels are selected (0.5 of the HBM peak at rho = 1).  Here, like the acquisition scorer (scorer.cu):
-//   * the unit of work is a STRIP ROW of 64 pixels (2 per lane; 16 warps per SM); strip rows are linearised (image, strip, y) and cut
-//     into one contiguous range per warp of a single-wave persistent grid, so a lane walks DOWN its four columns;
+//   * the unit of work is a STRIP ROW of 64 pixels (2 per lane; 16 warps per SM); strip rows are linearised (image, strip, y)
+//     and cut into one contiguous range per warp of a single-wave persistent grid, so a lane walks DOWN its two columns;
 //   * every warp runs its own ring of shared-memory stages; lane 0 issues one cp.async.bulk.tensor box
 //     {64 px, 1 row, C' planes} for the logits plus one each for the ids and the mask bytes of the row, completion on a
 //     per-stage mbarrier; the planes are then read with vector shared-memory loads at constant offsets (no per-plane
@@ -48,7 +48,7 @@ struct DenseMaps {
 };
 
 struct DenseShape {
-    int strips;               // 128-pixel strips per image row
+    int strips;               // strips (kStripPx pixels wide) per image row
     long long total_rows;     // n_img * strips * H
     int stages;
     uint32_t stage_bytes, tx_bytes, ids_off, mask_off;      // stage stride (128-byte multiple) / bytes one row's three boxes deliver
