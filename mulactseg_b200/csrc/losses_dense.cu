@@ -39,7 +39,11 @@ namespace {
 #endif
 constexpr int kPx = MAS_DENSE_PX;       // pixels per lane (2: 64-pixel strip rows, twice the warps per SM; 4: 128-pixel strip rows)
 constexpr int kStripPx = 32 * kPx;
+#ifdef MAS_DENSE_MAXWARPS
+constexpr int kMaxWarps = MAS_DENSE_MAXWARPS;      // comparison builds: fewer warps, more registers per thread
+#else
 constexpr int kMaxWarps = kPx == 2 ? 16 : 8;
+#endif
 constexpr int kPrivRanks = 3;           // private running maxima: the first three candidate classes of a superpixel
 constexpr uint32_t kFull = 0xffffffffu;
 
