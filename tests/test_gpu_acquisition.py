@@ -542,3 +542,25 @@ def test_selector_plugin_scores_from_the_low_resolution_head_when_asked():
     args.b200_lowres = True
     fused = plugin.RegionSelector(args).score_regions(trainer, pool).scores.cpu().numpy()
     np.testing.assert_allclose(fused, full, rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.parametrize("c,dtype", [(22, torch.float32), (24, torch.float32), (31, torch.float32), (22, torch.bfloat16)])
+def test_split_id_ring_equals_ids_in_the_stages(c, dtype, monkeypatch):
+    """TMA path, wide class counts: the id rows ride in one buffer per warp with its own barrier when that buys a warp
+    (C' >= 22 fp32).  Same histograms / sums as with the ids inside the logits stages, and as the oracle's histograms."""
+    from mulactseg_b200 import acquisition as acq
+    n, h, w, nseg = 5, 37, 384, 40                                      # several strips, rows not a multiple of anything
+    logits = synth.logits(n, c, h, w, "cosine", seed=c).to(dtype)
+    spx = synth.superpixel_map(n, h, w, nseg, "jitter", seed=c + 1, dtype=torch.int32)
+    out = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("MAS_SCORER_SPLIT_IDS", split)
+        stats = acq.RegionStats(n, nseg, c, DEV, need_prob=True, group_bytes=0)
+        stats.add_batch(0, logits.to(DEV), spx.to(DEV), 0.1)
+        out[split] = (stats.cls_cnt.clone(), stats.cls_sum.clone(), stats.prob_sum.clone())
+    assert torch.equal(out["0"][0], out["1"][0])
+    np.testing.assert_allclose(out["1"][1].cpu().numpy(), out["0"][1].cpu().numpy(), rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(out["1"][2].cpu().numpy(), out["0"][2].cpu().numpy(), rtol=1e-6)
+    ref = oa.region_histograms(batches(logits.float(), spx, n), nseg, 0.1).numpy()
+    if dtype == torch.float32:
+        np.testing.assert_array_equal(out["1"][0].cpu().numpy().astype(np.int64), ref)
